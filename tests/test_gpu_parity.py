@@ -1,0 +1,261 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the reference-shaped
+Python surface, against the CPU oracle (oracle/) and the golden fixtures produced by the unmodified
+reference (tests/golden, oracle/make_golden.py).
+
+Tolerances (floating point path; BASELINE.json north_star): mask max-abs < 1e-3 vs the CPU fp32
+reference; masked spectrogram compared in normalised units (|.| / max|X|) < 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import checksum
+
+pytestmark = pytest.mark.gpu
+
+MASK_TOL = 1e-3
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module')
+def default_model():
+    from lib import nets, synth
+    m = nets.CascadedNet(2048, 1024, 32, 128)
+    m.load_state_dict(synth.to_torch_state_dict(synth.make_state_dict()))
+    m.to(_dev())
+    return m
+
+
+@pytest.fixture(scope='module')
+def wave10():
+    from lib import synth
+    return synth.sine_mix(10.0)
+
+
+def test_stft_matches_oracle_and_golden(wave10, golden_default):
+    from lib import spec_utils
+    from oracle import stft_oracle
+    S = spec_utils.wave_to_spectrogram(wave10, 1024, 2048)
+    R = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    assert S.shape == R.shape and S.dtype == np.complex64
+    scale = np.abs(R).max()
+    assert np.abs(S - R).max() / scale < 5e-6
+    assert np.abs(S[:, ::16, :] - golden_default['X_sub']).max() / scale < 5e-6
+
+
+def test_istft_matches_oracle_and_roundtrip(wave10):
+    from lib import spec_utils
+    from oracle import stft_oracle
+    R = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    w = spec_utils.spectrogram_to_wave(R, 1024)
+    wr = stft_oracle.spectrogram_to_wave(R, 1024)
+    assert w.shape == wr.shape and w.dtype == np.float32
+    assert np.abs(w - wr).max() < 5e-6
+    assert np.abs(w - wave10[:, :w.shape[1]]).max() < 5e-6
+    w0 = spec_utils.spectrogram_to_wave(R[0], 1024)   # 2-D mono input (lib/spec_utils.py:158-159)
+    assert w0.shape == (w.shape[1],) and np.abs(w0 - wr[0]).max() < 5e-6
+
+
+def test_stft_ragged_and_small_fft():
+    from lib import spec_utils
+    from oracle import stft_oracle
+    rng = np.random.default_rng(3)
+    for n_fft, hop, L in ((512, 256, 5000), (2048, 1024, 1023), (2048, 1024, 2048), (1024, 256, 7777)):
+        x = rng.standard_normal((2, L)).astype(np.float32)
+        S = spec_utils.wave_to_spectrogram(x, hop, n_fft)
+        R = stft_oracle.wave_to_spectrogram(x, hop, n_fft)
+        assert S.shape == R.shape
+        assert np.abs(S - R).max() / np.abs(R).max() < 5e-6
+        if S.shape[2] > 1:
+            w = spec_utils.spectrogram_to_wave(R, hop)
+            wr = stft_oracle.spectrogram_to_wave(R, hop)
+            assert np.abs(w - wr).max() < 1e-5
+
+
+CONV_CASES = [
+    # N, Cin, H, W, Cout, k, stride, (dh, dw), act
+    (2, 2, 32, 32, 16, 3, 1, (1, 1), 1),
+    (1, 10, 16, 48, 32, 3, 1, (1, 1), 1),
+    (1, 16, 32, 32, 32, 3, 2, (1, 1), 2),
+    (1, 64, 16, 16, 64, 3, 1, (4, 2), 1),
+    (1, 64, 16, 16, 24, 3, 1, (12, 6), 1),
+    (2, 48, 8, 16, 8, 1, 1, (1, 1), 1),
+    (1, 25, 16, 32, 8, 3, 1, (1, 1), 0),
+]
+
+
+def _run_debug_conv(ctx, x, w, b, k, stride, dil, act, use_tc):
+    from lib import _native
+    N, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    dx, dw, db = x.cuda(), w.cuda(), b.cuda()
+    y = torch.empty((N, Cout, Ho, Wo), dtype=torch.float32, device='cuda')
+    ctx.check(ctx.lib.vr_debug_conv(ctx.handle, _native.ptr(dx), N, Cin, H, W, _native.ptr(dw), _native.ptr(db), Cout,
+                                    k, stride, dil[0], dil[1], act, use_tc, _native.ptr(y), _native.stream_ptr()),
+              'vr_debug_conv')
+    return y.cpu()
+
+
+def _ref_conv(x, w, b, k, stride, dil, act):
+    pad = (dil[0] * (k // 2), dil[1] * (k // 2))
+    y = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad, dilation=dil)
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
+        y = F.leaky_relu(y, 0.01)
+    return y.float()
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_cuda_core_kernel_vs_torch(case):
+    from lib import _native
+    N, Cin, H, W, Cout, k, stride, dil, act = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ctx = _native.Context(0, 2048, 1024, 32, 128, 256, 1, 1)
+    y = _run_debug_conv(ctx, x, w, b, k, stride, dil, act, 0)
+    ref = _ref_conv(x, w, b, k, stride, dil, act)
+    # storage is split-bf16 (16-bit significand): ~1.5e-5 relative on inputs and outputs
+    assert (y - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def _first_window(wave10):
+    from oracle import stft_oracle, separator_oracle
+    X = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    pad_l, pad_r, roi = separator_oracle.make_padding(X.shape[2], 256, 64)
+    Xp = np.pad(X, ((0, 0), (0, 0), (pad_l, pad_r)))
+    Xp /= np.abs(X).max()
+    return X, Xp
+
+
+def test_predict_mask_and_forward_vs_oracle(default_model, wave10):
+    from lib import synth
+    from oracle import net_oracle
+    _, Xp = _first_window(wave10)
+    x = np.abs(np.stack([Xp[:, :, 128:384], Xp[:, :, 256:512]]))
+    sd = synth.to_torch_state_dict(synth.make_state_dict())
+    ref = net_oracle.forward(sd, torch.from_numpy(x))
+    got = default_model.forward(torch.from_numpy(x).cuda()).cpu()
+    assert got.shape == ref.shape == (2, 2, 1025, 256)
+    assert (got - ref).abs().max().item() < MASK_TOL
+    got_c = default_model.predict_mask(torch.from_numpy(x).cuda()).cpu()
+    assert got_c.shape == (2, 2, 1025, 128)
+    assert (got_c - ref[:, :, :, 64:-64]).abs().max().item() < MASK_TOL
+    pred = default_model.predict(torch.from_numpy(x).cuda()).cpu()
+    assert (pred - (torch.from_numpy(x) * ref)[:, :, :, 64:-64]).abs().max().item() < MASK_TOL
+
+
+def test_separate_10s_vs_reference_golden(default_model, wave10, golden_default):
+    import inference
+    from oracle import stft_oracle
+    g = golden_default
+    X = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    sp = inference.Separator(default_model, _dev(), 4, 256, False)
+    X_before = X.copy()
+    y, v = sp.separate(X)
+    assert np.array_equal(X, X_before)            # caller's array is not mutated (inference.py:73-74)
+    assert y.dtype == np.complex64 and y.shape == X.shape and v.shape == X.shape
+    absmax = float(g['absmax'])
+    assert np.abs(y[:, ::16, :] - g['y_sub']).max() / absmax < MASK_TOL
+    # mask recovered from y = mask * X where |X| is not tiny
+    big = np.abs(X) > 1e-2 * absmax
+    mask = np.real(y * np.conj(X)) / np.maximum(np.abs(X) ** 2, 1e-20)
+    err = np.abs(mask[:, ::8, :] - g['mask_sub'])[big[:, ::8, :]].max()
+    assert err < MASK_TOL
+    assert np.abs(y + v - X).max() / absmax < 1e-6
+    cs = checksum(y)
+    assert abs(cs[2] - g['y_sum'][2]) / g['y_sum'][2] < 1e-3
+    # waves through the device inverse STFT
+    from lib import spec_utils
+    wy = spec_utils.spectrogram_to_wave(y, 1024)
+    assert np.abs(wy[:, ::16] - g['wave_inst_sub']).max() < 1e-3
+
+
+def test_mask_10s_direct_and_tta_vs_golden(default_model, wave10, golden_default):
+    import inference
+    from lib import _native
+    from oracle import stft_oracle
+    g = golden_default
+    X = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    sp = inference.Separator(default_model, _dev(), 3, 256, False)   # batch 3: 4 windows -> ragged last batch
+    d_spec = torch.from_numpy(X).cuda()
+    m = sp._mask_device(d_spec, False).cpu().numpy()
+    assert np.abs(m[:, ::8, :] - g['mask_sub']).max() < MASK_TOL
+    assert np.array_equal(m[:, 1024, :], m[:, 1023, :])           # replicate-padded Nyquist row (lib/nets.py:111-115)
+    mt = sp._mask_device(d_spec, True).cpu().numpy()
+    assert np.abs(mt[:, ::8, :] - g['mask_tta_sub']).max() < MASK_TOL
+    # the TTA normaliser is |lexicographic complex max|
+    ctx = sp._ctx()
+    out = torch.zeros(1, device='cuda')
+    ctx.check(ctx.lib.vr_normaliser(ctx.handle, _native.ptr(d_spec), X.shape[2], 1, _native.ptr(out),
+                                    _native.stream_ptr()), 'vr_normaliser')
+    assert abs(out.item() - abs(complex(g['tta_norm']))) < 1e-4 * abs(complex(g['tta_norm']))
+
+
+def test_private_separate_matches_oracle(default_model, wave10):
+    import inference
+    _, Xp = _first_window(wave10)
+    sp = inference.Separator(default_model, _dev(), 2, 256, False)
+    m = sp._separate(Xp.astype(np.complex64), 128)
+    from lib import synth
+    from oracle import separator_oracle
+    sd = synth.to_torch_state_dict(synth.make_state_dict())
+    ref = separator_oracle._separate(sd, Xp.astype(np.complex64), 128, 2048, 256, 64, 2)
+    assert m.shape == ref.shape
+    assert np.abs(m - ref).max() < MASK_TOL
+
+
+def test_separate_wave_fused_matches_staged(default_model, wave10, golden_default):
+    import inference
+    g = golden_default
+    sp = inference.Separator(default_model, _dev(), 4, 256, False)
+    inst, voc = sp.separate_wave(wave10)
+    assert inst.shape == (2, 440320) and voc.shape == inst.shape
+    assert np.abs(inst[:, ::16] - g['wave_inst_sub']).max() < 1e-3
+    assert np.abs(voc[:, ::16] - g['wave_voc_sub']).max() < 1e-3
+    d_inst, d_voc = sp.separate_wave(torch.from_numpy(wave10).cuda())
+    assert np.abs(d_inst.cpu().numpy() - inst).max() < 1e-6
+    # stems add up to the (round-tripped) mixture
+    assert np.abs(inst + voc - wave10[:, :inst.shape[1]]).max() < 1e-4
+
+
+def test_small_config_vs_reference_golden(golden_small):
+    import inference
+    from lib import nets, synth
+    from oracle import stft_oracle
+    m = nets.CascadedNet(512, 256, 16, 32)
+    m.load_state_dict(synth.to_torch_state_dict(synth.make_state_dict(512, 16, 32)))
+    m.to(_dev())
+    X = stft_oracle.wave_to_spectrogram(synth.sine_mix(3.0), 256, 512)
+    sp = inference.Separator(m, _dev(), 2, 192, False)
+    mask = sp._mask_device(torch.from_numpy(X).cuda(), False).cpu().numpy()
+    assert np.abs(mask[:, ::2, :] - golden_small['mask_sub']).max() < MASK_TOL
+
+
+def test_load_state_dict_is_strict():
+    from lib import nets, synth
+    m = nets.CascadedNet(2048, 1024, 32, 128)
+    sd = synth.to_torch_state_dict(synth.make_state_dict())
+    bad = dict(sd)
+    bad.pop('out.weight')
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+    bad = dict(sd)
+    bad['extra.weight'] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+    # the native library is strict on its own as well
+    from lib import _native
+    ctx = _native.Context(0, 2048, 1024, 32, 128, 256, 1)
+    bad = dict(sd)
+    bad.pop('aux_out.weight')
+    with pytest.raises(_native.NativeError):
+        ctx.load_state_dict(bad)

@@ -1,0 +1,172 @@
+// extern "C" surface of libvr_b200.so; declarations and the reference call each entry replaces are in
+// include/vr_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/vr_b200.h"
+#include "engine.h"
+
+struct vr_ctx {
+  vr::Engine* eng;
+  std::string err;
+};
+
+static std::string g_create_err;
+
+static int fail(vr_ctx* c, const std::string& m) {
+  if (c) c->err = m;
+  return -1;
+}
+static int done(vr_ctx* c, bool ok) {
+  if (ok) return 0;
+  c->err = c->eng->err;
+  return -1;
+}
+#define CHECK_CTX(c) \
+  if (!(c) || !(c)->eng) return -2;
+
+extern "C" {
+
+int vr_create(const vr_config* cfg, vr_ctx** out) {
+  if (!cfg || !out) return -2;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_err = "no CUDA device visible: libvr_b200 has no CPU path";
+    return -1;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_err = "invalid device ordinal";
+    return -1;
+  }
+  int nf = cfg->n_fft;
+  if (nf < 64 || nf > 4096 || (nf & (nf - 1))) {
+    g_create_err = "n_fft must be a power of two in [64, 4096]";
+    return -1;
+  }
+  if (cfg->hop_length <= 0 || cfg->hop_length > nf) {
+    g_create_err = "hop_length must be in (0, n_fft]";
+    return -1;
+  }
+  if (cfg->max_batch <= 0 || cfg->cropsize <= 0) {
+    g_create_err = "max_batch and cropsize must be positive";
+    return -1;
+  }
+  vr::Config c;
+  c.device = cfg->device; c.n_fft = cfg->n_fft; c.hop = cfg->hop_length; c.nout = cfg->nout;
+  c.nout_lstm = cfg->nout_lstm; c.cropsize = cfg->cropsize; c.max_batch = cfg->max_batch;
+  c.conv_mode = cfg->conv_mode;
+  vr_ctx* ctx = new vr_ctx();
+  ctx->eng = new vr::Engine(c);
+  if (!ctx->eng->err.empty()) {
+    g_create_err = ctx->eng->err;
+    delete ctx->eng;
+    delete ctx;
+    return -1;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void vr_destroy(vr_ctx* ctx) {
+  if (!ctx) return;
+  delete ctx->eng;
+  delete ctx;
+}
+
+const char* vr_last_error(const vr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int vr_load_tensor(vr_ctx* ctx, const char* name, int32_t dtype, int32_t ndim, const int64_t* shape,
+                   const void* host_data) {
+  CHECK_CTX(ctx);
+  if (!name || (!host_data) || ndim < 0 || ndim > 8) return fail(ctx, "vr_load_tensor: bad arguments");
+  return done(ctx, ctx->eng->load_tensor(name, dtype, ndim, shape, host_data));
+}
+
+int vr_finalize_weights(vr_ctx* ctx) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->finalize());
+}
+
+int vr_stft(vr_ctx* ctx, const float* wave, int64_t L, void* spec, int64_t T, float* absmax, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->stft(wave, L, (float2*)spec, T, absmax, (cudaStream_t)stream));
+}
+
+int vr_istft(vr_ctx* ctx, const void* spec, int64_t T, float* wave, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->istft((const float2*)spec, nullptr, T, wave, nullptr, (cudaStream_t)stream));
+}
+
+int vr_predict_mask(vr_ctx* ctx, const float* mag, int32_t N, float* mask, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->predict_mask(mag, N, mask, ctx->eng->cfg().offset, (cudaStream_t)stream));
+}
+
+int vr_forward(vr_ctx* ctx, const float* mag, int32_t N, float* mask, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->predict_mask(mag, N, mask, 0, (cudaStream_t)stream));
+}
+
+int vr_normaliser(vr_ctx* ctx, const void* spec, int64_t T, int32_t norm_mode, float* out, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->normaliser((const float2*)spec, T, norm_mode, out, (cudaStream_t)stream));
+}
+
+int vr_separate_windows(vr_ctx* ctx, const void* spec, int64_t T, const float* norm, int32_t pad_l,
+                        int32_t first_window, int32_t n_windows, float* mask, int64_t mask_T, int64_t frame_shift,
+                        int32_t accumulate, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->separate_windows((const float2*)spec, T, norm, pad_l, first_window, n_windows, mask,
+                                              mask_T, frame_shift, accumulate, (cudaStream_t)stream));
+}
+
+int vr_separate(vr_ctx* ctx, const void* spec, int64_t T, int32_t tta, float* mask, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->separate((const float2*)spec, T, tta, mask, (cudaStream_t)stream));
+}
+
+int vr_apply_mask(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, void* y_spec, void* v_spec,
+                  void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->apply_mask((const float2*)spec, mask, T, (float2*)y_spec, (float2*)v_spec,
+                                        (cudaStream_t)stream));
+}
+
+int vr_apply_mask_istft(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, float* wave_inst,
+                        float* wave_voc, void* stream) {
+  CHECK_CTX(ctx);
+  if (!mask) return fail(ctx, "vr_apply_mask_istft: mask is NULL");
+  return done(ctx, ctx->eng->istft((const float2*)spec, mask, T, wave_inst, wave_voc, (cudaStream_t)stream));
+}
+
+int vr_separate_wave(vr_ctx* ctx, const float* wave, int64_t L, int32_t tta, float* wave_inst, float* wave_voc,
+                     void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->separate_wave(wave, L, tta, wave_inst, wave_voc, (cudaStream_t)stream));
+}
+
+int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_t tta, float* inst_host,
+                          float* voc_host, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->separate_wave_host(wave_host, L, tta, inst_host, voc_host, (cudaStream_t)stream));
+}
+
+int64_t vr_launch_count(const vr_ctx* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
+
+int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w,
+                  const float* bias, int32_t Cout, int32_t k, int32_t stride, int32_t dil_h, int32_t dil_w, int32_t act,
+                  int32_t use_tc, float* y, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->debug_conv(x, N, Cin, H, W, w, bias, Cout, k, stride, dil_h, dil_w, act, use_tc, y,
+                                        (cudaStream_t)stream));
+}
+
+int vr_debug_read(vr_ctx* ctx, const char* what, float* out, int64_t capacity, int64_t* dims, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->debug_read(what, out, capacity, dims, (cudaStream_t)stream));
+}
+
+}  // extern "C"

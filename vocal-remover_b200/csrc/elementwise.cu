@@ -1,0 +1,390 @@
+// Bandwidth-bound kernels of the CascadedNet forward and the Separator glue (HBM roofline).
+//   pack_mag_*      inference.py:44-50,58-60 (window gather + |X|) and inference.py:74 (normalise)
+//   upsample2x      lib/layers.py:52  F.interpolate(x2, bilinear, align_corners=True), written into the concat slice
+//   pool_freq_mean  lib/layers.py:71  AdaptiveAvgPool2d((1, None))
+//   broadcast_rows  lib/layers.py:94  bilinear resize from height 1 == exact broadcast
+//   mask_out        lib/nets.py:79,109-115,127-129  1x1 conv -> sigmoid -> replicate Nyquist row -> crop offset
+//   absmax / lexmax inference.py:74 / inference.py:87,94 global normalisers
+//   apply_mask      inference.py:32-36
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vr {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_mag_from_spec_kernel(const float2* __restrict__ spec, int bins, int64_t T, int max_bin, int W,
+                                          int roi, int pad_l, int first_window, const float* __restrict__ norm,
+                                          ActView dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)dst.N * max_bin * W;
+  if (idx >= total) return;
+  int tw = (int)(idx % W);
+  int64_t r = idx / W;
+  int bin = (int)(r % max_bin);
+  int n = (int)(r / max_bin);
+  int64_t t = (int64_t)(first_window + n) * roi + tw - pad_l;
+  float inv = 1.0f / *norm;
+  float m0 = 0.f, m1 = 0.f;
+  if (t >= 0 && t < T) {
+    float2 a = spec[((int64_t)0 * bins + bin) * T + t];
+    float2 b = spec[((int64_t)1 * bins + bin) * T + t];
+    m0 = hypotf(a.x, a.y) * inv;
+    m1 = hypotf(b.x, b.y) * inv;
+  }
+  int64_t off = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)tw * dst.sw;
+  bf16 h0, l0, h1, l1;
+  split_bf16(m0, h0, l0);
+  split_bf16(m1, h1, l1);
+  *reinterpret_cast<__nv_bfloat162*>(dst.hi + off) = __halves2bfloat162(h0, h1);
+  *reinterpret_cast<__nv_bfloat162*>(dst.lo + off) = __halves2bfloat162(l0, l1);
+}
+
+cudaError_t launch_pack_mag_from_spec(const float2* spec, int bins, int64_t T, int max_bin, int W, int roi,
+                                      int pad_l, int first_window, const float* norm, ActView dst,
+                                      cudaStream_t stream) {
+  int64_t total = (int64_t)dst.N * max_bin * W;
+  if (total == 0) return cudaSuccess;
+  pack_mag_from_spec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(spec, bins, T, max_bin, W, roi,
+                                                                                 pad_l, first_window, norm, dst);
+  return cudaGetLastError();
+}
+
+__global__ void pack_mag_from_float_kernel(const float* __restrict__ mag, int bins, int max_bin, ActView dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int W = dst.W;
+  int64_t total = (int64_t)dst.N * max_bin * W;
+  if (idx >= total) return;
+  int tw = (int)(idx % W);
+  int64_t r = idx / W;
+  int bin = (int)(r % max_bin);
+  int n = (int)(r / max_bin);
+  float m0 = mag[(((int64_t)n * 2 + 0) * bins + bin) * W + tw];
+  float m1 = mag[(((int64_t)n * 2 + 1) * bins + bin) * W + tw];
+  int64_t off = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)tw * dst.sw;
+  bf16 h0, l0, h1, l1;
+  split_bf16(m0, h0, l0);
+  split_bf16(m1, h1, l1);
+  *reinterpret_cast<__nv_bfloat162*>(dst.hi + off) = __halves2bfloat162(h0, h1);
+  *reinterpret_cast<__nv_bfloat162*>(dst.lo + off) = __halves2bfloat162(l0, l1);
+}
+
+cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, ActView dst, cudaStream_t stream) {
+  int64_t total = (int64_t)dst.N * max_bin * dst.W;
+  if (total == 0) return cudaSuccess;
+  pack_mag_from_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(mag, bins, max_bin, dst);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One thread per (output pixel, 8-channel chunk).  Source index and weights follow ATen's
+// upsample_bilinear2d with align_corners=True: scale = (in-1)/(out-1) in fp32, src = scale*dst.
+__global__ void upsample2x_kernel(ActView in, ActView out) {
+  const int chunks = in.C >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)out.N * out.H * out.W * chunks;
+  if (idx >= total) return;
+  int ck = (int)(idx % chunks);
+  int64_t r = idx / chunks;
+  int wo = (int)(r % out.W);
+  r /= out.W;
+  int ho = (int)(r % out.H);
+  int n = (int)(r / out.H);
+  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
+  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  float fy = sh * ho, fx = sw * wo;
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
+  float ly = fy - y0, lx = fx - x0;
+  float hy = 1.f - ly, hx = 1.f - lx;
+  const int64_t base = (int64_t)n * in.sn + ck * 8;
+  float a[8], b[8], c[8], d[8], y[8];
+  int64_t o00 = base + (int64_t)y0 * in.sh + (int64_t)x0 * in.sw;
+  int64_t o01 = base + (int64_t)y0 * in.sh + (int64_t)x1 * in.sw;
+  int64_t o10 = base + (int64_t)y1 * in.sh + (int64_t)x0 * in.sw;
+  int64_t o11 = base + (int64_t)y1 * in.sh + (int64_t)x1 * in.sw;
+  load8(in.hi + o00, in.lo + o00, a);
+  load8(in.hi + o01, in.lo + o01, b);
+  load8(in.hi + o10, in.lo + o10, c);
+  load8(in.hi + o11, in.lo + o11, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+  int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * 8;
+  bf16x8 h, l;
+  split8(y, h, l);
+  *reinterpret_cast<bf16x8*>(out.hi + oo) = h;
+  *reinterpret_cast<bf16x8*>(out.lo + oo) = l;
+}
+
+cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
+  int64_t total = (int64_t)out.N * out.H * out.W * (in.C >> 3);
+  if (total == 0) return cudaSuccess;
+  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pool_freq_mean_kernel(ActView in, ActView out) {
+  const int chunks = in.C >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)in.N * in.W * chunks;
+  if (idx >= total) return;
+  int ck = (int)(idx % chunks);
+  int64_t r = idx / chunks;
+  int w = (int)(r % in.W);
+  int n = (int)(r / in.W);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int h = 0; h < in.H; ++h) {
+    float x[8];
+    int64_t o = (int64_t)n * in.sn + (int64_t)h * in.sh + (int64_t)w * in.sw + ck * 8;
+    load8(in.hi + o, in.lo + o, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += x[i];
+  }
+  const float inv = 1.f / (float)in.H;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  int64_t oo = (int64_t)n * out.sn + (int64_t)w * out.sw + ck * 8;
+  bf16x8 hh, ll;
+  split8(acc, hh, ll);
+  *reinterpret_cast<bf16x8*>(out.hi + oo) = hh;
+  *reinterpret_cast<bf16x8*>(out.lo + oo) = ll;
+}
+
+cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream) {
+  int64_t total = (int64_t)in.N * in.W * (in.C >> 3);
+  if (total == 0) return cudaSuccess;
+  pool_freq_mean_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(in, out);
+  return cudaGetLastError();
+}
+
+__global__ void broadcast_rows_kernel(ActView in, ActView out) {
+  const int chunks = in.C >> 3;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)out.N * out.H * out.W * chunks;
+  if (idx >= total) return;
+  int ck = (int)(idx % chunks);
+  int64_t r = idx / chunks;
+  int w = (int)(r % out.W);
+  r /= out.W;
+  int h = (int)(r % out.H);
+  int n = (int)(r / out.H);
+  int64_t oi = (int64_t)n * in.sn + (int64_t)w * in.sw + ck * 8;
+  int64_t oo = (int64_t)n * out.sn + (int64_t)h * out.sh + (int64_t)w * out.sw + ck * 8;
+  *reinterpret_cast<bf16x8*>(out.hi + oo) = *reinterpret_cast<const bf16x8*>(in.hi + oi);
+  *reinterpret_cast<bf16x8*>(out.lo + oo) = *reinterpret_cast<const bf16x8*>(in.lo + oi);
+}
+
+cudaError_t launch_broadcast_rows(ActView in, ActView out, cudaStream_t stream) {
+  int64_t total = (int64_t)out.N * out.H * out.W * (in.C >> 3);
+  if (total == 0) return cudaSuccess;
+  broadcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Final 1x1 conv (nout -> 2, no BN) + sigmoid, only for the frames that survive the offset crop.
+template <int NOUT>
+__global__ void mask_out_kernel(MaskOutParams p) {
+  const int roi = p.f3.W - 2 * p.offset;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)p.f3.N * p.f3.H * roi;
+  if (idx >= total) return;
+  int tr = (int)(idx % roi);
+  int64_t r = idx / roi;
+  int bin = (int)(r % p.f3.H);
+  int n = (int)(r / p.f3.H);
+  int64_t t = p.t_base0 + (int64_t)n * p.roi_t + tr;
+  if (t < 0 || t >= p.t_limit) return;
+  int64_t o = (int64_t)n * p.f3.sn + (int64_t)bin * p.f3.sh + (int64_t)(tr + p.offset) * p.f3.sw;
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NOUT; c += 8) {
+    float x[8];
+    load8(p.f3.hi + o + c, p.f3.lo + o + c, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0 = fmaf(x[i], __ldg(p.w + c + i), a0);
+      a1 = fmaf(x[i], __ldg(p.w + NOUT + c + i), a1);
+    }
+  }
+  float m0 = 1.f / (1.f + expf(-a0));
+  float m1 = 1.f / (1.f + expf(-a1));
+  float* d0 = p.out + (int64_t)n * p.stride_n + (int64_t)bin * p.stride_bin + p.t_base0 + tr;
+  float* d1 = d0 + p.stride_c;
+  const bool last = bin == p.f3.H - 1;   // F.pad(..., mode='replicate') of the Nyquist row (lib/nets.py:111-115)
+  if (p.accumulate) {
+    *d0 = (*d0 + m0) * 0.5f;
+    *d1 = (*d1 + m1) * 0.5f;
+    if (last) {
+      d0[p.stride_bin] = (d0[p.stride_bin] + m0) * 0.5f;
+      d1[p.stride_bin] = (d1[p.stride_bin] + m1) * 0.5f;
+    }
+  } else {
+    *d0 = m0;
+    *d1 = m1;
+    if (last) {
+      d0[p.stride_bin] = m0;
+      d1[p.stride_bin] = m1;
+    }
+  }
+}
+
+cudaError_t launch_mask_out(const MaskOutParams& p, cudaStream_t stream) {
+  const int roi = p.f3.W - 2 * p.offset;
+  int64_t total = (int64_t)p.f3.N * p.f3.H * roi;
+  if (total <= 0) return cudaSuccess;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  switch (p.f3.C) {
+    case 8: mask_out_kernel<8><<<grid, 256, 0, stream>>>(p); break;
+    case 16: mask_out_kernel<16><<<grid, 256, 0, stream>>>(p); break;
+    case 32: mask_out_kernel<32><<<grid, 256, 0, stream>>>(p); break;
+    case 64: mask_out_kernel<64><<<grid, 256, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float2* __restrict__ spec, int64_t n, float* out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 v = spec[i];
+    m = fmaxf(m, hypotf(v.x, v.y));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));  // m >= 0
+  }
+}
+
+cudaError_t launch_absmax(const float2* spec, int64_t n, float* out_absmax, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out_absmax, 0, sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  int grid = (int)(((n + 255) / 256) < 148 * 8 ? ((n + 255) / 256) : 148 * 8);
+  absmax_kernel<<<grid, 256, 0, stream>>>(spec, n, out_absmax);
+  return cudaGetLastError();
+}
+
+// numpy's max() of a complex array is lexicographic (largest real part, ties by imaginary part);
+// separate_tta divides by that complex number (inference.py:87,94), so the net sees |X| / |lexmax|.
+__device__ __forceinline__ unsigned int order_key(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float order_unkey(unsigned int k) {
+  unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__global__ void lexmax_kernel(const float2* __restrict__ spec, int64_t n, unsigned long long* scratch) {
+  unsigned long long best = 0ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 v = spec[i];
+    unsigned long long k = ((unsigned long long)order_key(v.x) << 32) | order_key(v.y);
+    best = k > best ? k : best;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(scratch, best);
+}
+
+__global__ void lexmax_finish_kernel(const unsigned long long* scratch, float* out_norm) {
+  unsigned long long k = *scratch;
+  float re = order_unkey((unsigned int)(k >> 32));
+  float im = order_unkey((unsigned int)(k & 0xffffffffu));
+  // the zero padding of X_spec_pad also takes part in the max (inference.py:86-87)
+  unsigned long long kz = ((unsigned long long)order_key(0.f) << 32) | order_key(0.f);
+  if (kz > k) { re = 0.f; im = 0.f; }
+  *out_norm = hypotf(re, im);
+}
+
+cudaError_t launch_lexmax_abs(const float2* spec, int64_t n, unsigned long long* scratch, float* out_norm,
+                              cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    int grid = (int)(((n + 255) / 256) < 148 * 8 ? ((n + 255) / 256) : 148 * 8);
+    lexmax_kernel<<<grid, 256, 0, stream>>>(spec, n, scratch);
+  }
+  lexmax_finish_kernel<<<1, 1, 0, stream>>>(scratch, out_norm);
+  return cudaGetLastError();
+}
+
+__global__ void apply_mask_kernel(const float2* __restrict__ spec, const float* __restrict__ mask, int64_t n,
+                                  float2* __restrict__ y, float2* __restrict__ v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 x = spec[i];
+  float m = mask[i];
+  y[i] = make_float2(m * x.x, m * x.y);
+  float q = 1.f - m;
+  v[i] = make_float2(q * x.x, q * x.y);
+}
+
+cudaError_t launch_apply_mask(const float2* spec, const float* mask, int64_t n, float2* y, float2* v,
+                              cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  apply_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(spec, mask, n, y, v);
+  return cudaGetLastError();
+}
+
+}  // namespace vr
+
+// ------------------------------------------------------------------------------------------------
+// Layout converters used by the API-parity entry points and the tests (NCHW fp32 <-> NHWC split-bf16).
+namespace vr {
+
+__global__ void nchw_to_act_kernel(const float* __restrict__ x, int C, ActView dst) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)dst.N * dst.H * dst.W * dst.C;
+  if (idx >= total) return;
+  int c = (int)(idx % dst.C);
+  int64_t r = idx / dst.C;
+  int w = (int)(r % dst.W);
+  r /= dst.W;
+  int h = (int)(r % dst.H);
+  int n = (int)(r / dst.H);
+  float v = c < C ? x[(((int64_t)n * C + c) * dst.H + h) * dst.W + w] : 0.f;
+  int64_t o = (int64_t)n * dst.sn + (int64_t)h * dst.sh + (int64_t)w * dst.sw + c;
+  split_bf16(v, dst.hi[o], dst.lo[o]);
+}
+
+cudaError_t launch_nchw_to_act(const float* x, int C, ActView dst, cudaStream_t stream) {
+  int64_t total = (int64_t)dst.N * dst.H * dst.W * dst.C;
+  if (total == 0) return cudaSuccess;
+  nchw_to_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, C, dst);
+  return cudaGetLastError();
+}
+
+__global__ void act_to_nchw_kernel(ActView src, int C, float* __restrict__ y) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)src.N * C * src.H * src.W;
+  if (idx >= total) return;
+  int w = (int)(idx % src.W);
+  int64_t r = idx / src.W;
+  int h = (int)(r % src.H);
+  r /= src.H;
+  int c = (int)(r % C);
+  int n = (int)(r / C);
+  int64_t o = (int64_t)n * src.sn + (int64_t)h * src.sh + (int64_t)w * src.sw + c;
+  y[idx] = join_bf16(src.hi[o], src.lo[o]);
+}
+
+cudaError_t launch_act_to_nchw(ActView src, int C, float* y, cudaStream_t stream) {
+  int64_t total = (int64_t)src.N * C * src.H * src.W;
+  if (total == 0) return cudaSuccess;
+  act_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, C, y);
+  return cudaGetLastError();
+}
+
+}  // namespace vr

@@ -1,0 +1,164 @@
+// Host-side engine: owns the device arena, the packed checkpoint and the per-layer launch plan of
+// the CascadedNet forward (reference lib/nets.py:44-141) and the Separator glue (inference.py:16-102).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vr {
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct Buffer {   // a whole NHWC split-bf16 allocation
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  ActView view(int n, int h0, int h, int c0, int c) const {
+    ActView v;
+    const int64_t off = (int64_t)h0 * W * C + c0;
+    v.hi = hi + off;
+    v.lo = lo + off;
+    v.N = n; v.H = h; v.W = W; v.C = c;
+    v.sn = (int64_t)H * W * C;
+    v.sh = (int64_t)W * C;
+    v.sw = C;
+    return v;
+  }
+  ActView all(int n) const { return view(n, 0, H, 0, C); }
+};
+
+struct TcConv;   // tcgen05 plan (conv_tc.cu)
+
+struct ConvLayer {
+  std::string name;
+  int Cin = 0, CinPad = 0, Cout = 0, CoutPad = 0;
+  int k = 1, stride = 1, dil_h = 1, dil_w = 1, act = ACT_RELU;
+  float* w = nullptr;      // device fp32 [taps][CinPad][CoutPad]
+  float* bias = nullptr;   // device fp32 [CoutPad]
+  std::vector<float> w_host;     // packed copy kept for the tensor-core packer
+  std::vector<float> bias_host;
+  std::shared_ptr<TcConv> tc;    // null -> CUDA-core kernel
+};
+
+struct LstmPlan {
+  int C = 0, bins = 0, hid = 0, T = 0;
+  float* conv_w = nullptr;   // [C] folded
+  float conv_bias = 0.f;
+  float* wih = nullptr;      // [8*hid][bins]  (forward rows then reverse rows)
+  float* bih = nullptr;      // [8*hid]        bias_ih + bias_hh
+  float* whh = nullptr;      // [2][4*hid][hid]
+  float* wdT = nullptr;      // [2*hid][bins]
+  float* dscale = nullptr;   // [bins]  BatchNorm1d scale
+  float* dshift = nullptr;   // [bins]  scale*linear_bias + BatchNorm1d shift
+  float* l0 = nullptr;       // [N][T][bins]
+  float* xp = nullptr;       // [N][T][8*hid]
+  float* hs = nullptr;       // [N][T][2*hid]
+};
+
+struct BaseNetPlan {
+  std::string prefix;
+  int n = 0, H = 0, W = 0;
+  ConvLayer enc1, enc_a[4], enc_b[4], aspp1, aspp2, aspp_d[3], bott, dec[4];   // dec[0]=dec4 .. dec[3]=dec1
+  LstmPlan lstm;
+  Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2;
+  int e1_off = 0;   // channel offset of e1 inside cat1
+};
+
+struct Config {
+  int device = 0;
+  int n_fft = 2048, hop = 1024, nout = 32, nout_lstm = 128, cropsize = 256, max_batch = 4;
+  int offset = 64;
+  int conv_mode = 0;   // 0: tcgen05 where eligible, 1: CUDA-core kernel everywhere (validation)
+};
+
+class Engine {
+ public:
+  explicit Engine(const Config& cfg);
+  ~Engine();
+
+  std::string err;
+
+  bool load_tensor(const char* name, int dtype, int ndim, const int64_t* shape, const void* data);
+  bool finalize();
+  bool ready() const { return finalized_; }
+
+  // ---- reference-surface operations (device pointers) ----
+  bool stft(const float* wave, int64_t L, float2* spec, int64_t T, float* absmax, cudaStream_t s);
+  bool istft(const float2* spec, const float* mask, int64_t T, float* wave_a, float* wave_b, cudaStream_t s);
+  bool predict_mask(const float* mag, int N, float* mask_out, int offset, cudaStream_t s);
+  // windows [first, first+count) of the padded spectrogram -> mask frames; see include/vr_b200.h
+  bool separate_windows(const float2* spec, int64_t T, const float* norm, int pad_l, int first, int count,
+                        float* mask, int64_t mask_T, int64_t frame_shift, int accumulate, cudaStream_t s);
+  bool separate(const float2* spec, int64_t T, int tta, float* mask, cudaStream_t s);
+  bool apply_mask(const float2* spec, const float* mask, int64_t T, float2* y, float2* v, cudaStream_t s);
+  bool separate_wave(const float* wave, int64_t L, int tta, float* inst, float* voc, cudaStream_t s);
+  bool separate_wave_host(const float* wave, int64_t L, int tta, float* inst, float* voc, cudaStream_t s);
+  bool normaliser(const float2* spec, int64_t T, int mode, float* out, cudaStream_t s);
+
+  // debug / tests: run one reference Conv2DBNActiv-shaped layer through a chosen kernel
+  bool debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const float* w, const float* bias, int Cout,
+                  int k, int stride, int dil_h, int dil_w, int act, int use_tc, float* y_nchw, cudaStream_t s);
+  // debug: copy an internal activation (by name) of the last forward to NCHW fp32
+  bool debug_read(const char* what, float* out, int64_t cap, int64_t* dims, cudaStream_t s);
+
+  const Config& cfg() const { return cfg_; }
+  int bins() const { return cfg_.n_fft / 2 + 1; }
+  int roi() const { int r = cfg_.cropsize - 2 * cfg_.offset; return r == 0 ? cfg_.cropsize : r; }
+  int64_t launches = 0;   // kernels launched by this engine (bench 'gpu_launches')
+
+ private:
+  Config cfg_;
+  bool finalized_ = false;
+  std::map<std::string, HostTensor> sd_;
+  std::vector<void*> allocs_;
+  int last_n_ = 0;
+
+  // whole-track workspace (grow-only)
+  float2* ws_spec_ = nullptr; int64_t ws_spec_cap_ = 0;
+  float* ws_mask_ = nullptr; int64_t ws_mask_cap_ = 0;
+  float* ws_frames_ = nullptr; int64_t ws_frames_cap_ = 0;
+  float* ws_wave_ = nullptr; int64_t ws_wave_cap_ = 0;   // [2][L] in + 2 x [2][Lo] out (host-buffer entry)
+  float* ws_norm_ = nullptr;            // [4] floats: absmax, lexmax-abs
+  unsigned long long* ws_lex_ = nullptr;
+
+  float2* twiddle_ = nullptr;
+  float* window_ = nullptr;
+
+  Buffer in3_;                 // (Nb, max_bin, W, C3): [aux2 | aux1 | x | pad]
+  int pos_aux2_ = 0, pos_aux1_ = 0, pos_x_ = 0;
+  Buffer o1_, o2_;             // low-band BaseNet outputs before the 1x1 bridge (stage 1 / stage 2)
+  Buffer f3_;                  // stage-3 output (Nb, max_bin, W, nout)
+  BaseNetPlan nets_[5];        // stg1_low, stg1_high, stg2_low, stg2_high, stg3_full
+  ConvLayer bridge1_, bridge2_;
+  float* out_w_ = nullptr;     // [2][nout]
+
+  void* dalloc(size_t bytes);
+  Buffer make_buffer(int N, int H, int W, int C);
+  bool need(const std::string& key, std::initializer_list<int64_t> shape, const HostTensor** out);
+  bool make_conv(ConvLayer& L, const std::string& prefix, const std::vector<int>& perm, int cin_pad, int k, int stride,
+                 int dh, int dw, int act);
+  bool build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, const std::vector<int>& in_perm, int cin_pad,
+                     int n, int H, int W, int nin_lstm, int nout_lstm);
+  bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s);
+  bool run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s);
+  bool forward(int N, cudaStream_t s);   // in3_ x-channels already packed for N windows -> f3_
+  bool ensure_ws(int64_t T);
+  bool ck(cudaError_t e, const char* what);
+};
+
+// conv_tc.cu
+bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out);
+bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs);
+cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err);
+
+}  // namespace vr

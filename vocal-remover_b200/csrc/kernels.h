@@ -1,0 +1,69 @@
+// Host-side launch prototypes for the hand-written sm_100a kernels of the hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace vr {
+
+// ---- convolution (conv_simt.cu / conv_tc.cu) -------------------------------------------------
+cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t stream);
+
+// ---- bandwidth kernels (elementwise.cu) ------------------------------------------------------
+// |X|/norm of window g = first_window + n, frame tw -> dst channels [0,2) ; spec is complex64 [2][bins][T]
+cudaError_t launch_pack_mag_from_spec(const float2* spec, int bins, int64_t T, int max_bin, int W, int roi,
+                                      int pad_l, int first_window, const float* norm, ActView dst,
+                                      cudaStream_t stream);
+// mag is float32 NCHW [N][2][bins][W] (the reference predict_mask input, lib/nets.py:124)
+cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, ActView dst, cudaStream_t stream);
+cudaError_t launch_nchw_to_act(const float* x, int C, ActView dst, cudaStream_t stream);
+cudaError_t launch_act_to_nchw(ActView src, int C, float* y, cudaStream_t stream);
+cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream);
+cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream);
+cudaError_t launch_broadcast_rows(ActView in, ActView out, cudaStream_t stream);
+
+struct MaskOutParams {
+  ActView f3;          // (N, max_bin, W, nout)
+  const float* w;      // [2][nout]  (CascadedNet.out.weight, lib/nets.py:79)
+  float* out;
+  int64_t stride_n, stride_c, stride_bin;  // element strides of the destination; frames are contiguous
+  int offset;          // model.offset (64): frames [offset, W-offset) are kept (lib/nets.py:127-129)
+  int64_t t_base0;     // destination frame index of frame `offset` of window 0, before stride_n is applied
+  int64_t t_limit;     // frames with (t_base0 + n*roi_t + tw-offset) outside [0, t_limit) are dropped
+  int roi_t;           // per-window frame advance used only for the limit test
+  int accumulate;      // 1: out = (out + mask) * 0.5  (TTA average, inference.py:98)
+};
+cudaError_t launch_mask_out(const MaskOutParams& p, cudaStream_t stream);
+
+cudaError_t launch_absmax(const float2* spec, int64_t n, float* out_absmax, cudaStream_t stream);
+cudaError_t launch_lexmax_abs(const float2* spec, int64_t n, unsigned long long* scratch, float* out_norm,
+                              cudaStream_t stream);
+cudaError_t launch_apply_mask(const float2* spec, const float* mask, int64_t n, float2* y, float2* v,
+                              cudaStream_t stream);
+
+// ---- LSTM branch (lstm.cu), reference lib/layers.py:108-133 ------------------------------------
+// 1x1 conv (C -> 1) + BN + ReLU, written time-major fp32: out[n][t][bin]
+cudaError_t launch_lstm_inconv(ActView in, const float* w, float bias, float* out, cudaStream_t stream);
+// C[M][N] = A[M][K] * B[N][K]^T + bias[N]
+cudaError_t launch_gemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                           cudaStream_t stream);
+// xp: [n][t][2][4*hid] gate pre-activations (input projection + both biases), whh: [2][4*hid][hid]
+// hs: [n][t][2*hid]
+cudaError_t launch_lstm_recurrence(const float* xp, const float* whh, float* hs, int N, int T, int hid,
+                                   cudaStream_t stream);
+// y = relu(scale * (hs . wd^T) + shift) scattered to channel `ch` of dst: dst[n][bin][t][ch]
+cudaError_t launch_lstm_dense(const float* hs, const float* wd, const float* scale, const float* shift, int N, int T,
+                              int K, int bins, ActView dst, int ch, cudaStream_t stream);
+
+// ---- STFT / iSTFT (fft.cu), reference lib/spec_utils.py:26-31,157-165 (librosa semantics)
+cudaError_t launch_stft(const float* wave, int64_t L, int n_fft, int hop, float2* spec, int64_t T,
+                        const float2* twiddle, const float* window, cudaStream_t stream);
+// frames_a[c][t][:] = hann * irfft(spec * mask), frames_b = hann * irfft(spec * (1 - mask));
+// mask == nullptr: frames_a = hann * irfft(spec), frames_b unused
+cudaError_t launch_istft_frames(const float2* spec, const float* mask, int n_fft, int64_t T, float* frames_a,
+                                float* frames_b, const float2* twiddle, const float* window, cudaStream_t stream);
+// overlap-add + window-sum-square normalisation + centre trim -> wave [2][hop*(T-1)]
+cudaError_t launch_istft_ola(const float* frames_a, const float* frames_b, int n_fft, int hop, int64_t T,
+                             float* wave_a, float* wave_b, const float* window, cudaStream_t stream);
+
+}  // namespace vr
