@@ -108,6 +108,11 @@ VR_API int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L,
 /* Number of kernels launched by this context so far (bench.py 'gpu_launches').                           */
 VR_API int64_t vr_launch_count(const vr_ctx* ctx);
 
+/* CUDA-event timing of every convolution launch between enable(1) and read (bench.py roofline):
+ * out[0..2] = tensor-core conv {ms, algorithmic FLOPs, launches}, out[3..5] = CUDA-core conv likewise.    */
+VR_API int vr_profile_enable(vr_ctx* ctx, int32_t on);
+VR_API int vr_profile_read(vr_ctx* ctx, double* out6);
+
 /* ---- validation hooks used by tests/ (not part of the reference surface) ---------------------------- */
 /* One Conv2DBNActiv-shaped layer (lib/layers.py:8-26; BN already folded into w/bias by the caller):
  * x [N][Cin][H][W] -> y [N][Cout][Ho][Wo]; use_tc selects the tcgen05 kernel (error if tile does not fit). */

@@ -156,6 +156,17 @@ int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_
 
 int64_t vr_launch_count(const vr_ctx* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
 
+int vr_profile_enable(vr_ctx* ctx, int32_t on) {
+  CHECK_CTX(ctx);
+  ctx->eng->profile_enable(on != 0);
+  return 0;
+}
+
+int vr_profile_read(vr_ctx* ctx, double* out6) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->profile_read(out6));
+}
+
 int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w,
                   const float* bias, int32_t Cout, int32_t k, int32_t stride, int32_t dil_h, int32_t dil_w, int32_t act,
                   int32_t use_tc, float* y, void* stream) {

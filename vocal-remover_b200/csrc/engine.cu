@@ -396,9 +396,51 @@ bool Engine::finalize() {
 }
 
 // ---------------------------------------------------------------------------------------------
+void Engine::profile_enable(bool on) {
+  for (auto& r : prof_) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  prof_.clear();
+  profiling_ = on;
+}
+
+bool Engine::profile_read(double* out6) {
+  for (int i = 0; i < 6; ++i) out6[i] = 0.0;
+  for (auto& r : prof_) {
+    if (!ck(cudaEventSynchronize(r.b), "profile sync")) return false;
+    float ms = 0.f;
+    if (!ck(cudaEventElapsedTime(&ms, r.a, r.b), "profile elapsed")) return false;
+    const int o = r.tc ? 0 : 3;
+    out6[o] += ms;
+    out6[o + 1] += r.flops;
+    out6[o + 2] += 1.0;
+  }
+  return true;
+}
+
 bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s) {
   ++launches;
-  if (L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out)) return ck(tc_launch(L, in, out, s, err), L.name.c_str());
+  const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
+  ProfRec rec;
+  if (profiling_) {
+    cudaEventCreate(&rec.a);
+    cudaEventCreate(&rec.b);
+    rec.tc = use_tc ? 1 : 0;
+    // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
+    rec.flops = 2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k;
+    cudaEventRecord(rec.a, s);
+  }
+  bool ok = run_conv_inner(L, in, out, use_tc, s);
+  if (profiling_) {
+    cudaEventRecord(rec.b, s);
+    prof_.push_back(rec);
+  }
+  return ok;
+}
+
+bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s) {
+  if (use_tc) return ck(tc_launch(L, in, out, s, err), L.name.c_str());
   ConvParams p;
   p.in = in; p.out = out;
   p.w = L.w; p.bias = L.bias;

@@ -116,12 +116,21 @@ class Engine {
   int roi() const { int r = cfg_.cropsize - 2 * cfg_.offset; return r == 0 ? cfg_.cropsize : r; }
   int64_t launches = 0;   // kernels launched by this engine (bench 'gpu_launches')
 
+  // optional CUDA-event timing of every convolution launch (bench.py roofline object)
+  void profile_enable(bool on);
+  // sums over the events recorded since enable: [0] tensor-core conv ms, [1] tensor-core conv algorithmic FLOPs,
+  // [2] tensor-core launches, [3] CUDA-core conv ms, [4] CUDA-core conv FLOPs, [5] CUDA-core launches
+  bool profile_read(double* out6);
+
  private:
   Config cfg_;
   bool finalized_ = false;
   std::map<std::string, HostTensor> sd_;
   std::vector<void*> allocs_;
   int last_n_ = 0;
+  struct ProfRec { cudaEvent_t a, b; double flops; int tc; };
+  bool profiling_ = false;
+  std::vector<ProfRec> prof_;
 
   // whole-track workspace (grow-only)
   float2* ws_spec_ = nullptr; int64_t ws_spec_cap_ = 0;
@@ -150,6 +159,7 @@ class Engine {
   bool build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, const std::vector<int>& in_perm, int cin_pad,
                      int n, int H, int W, int nin_lstm, int nout_lstm);
   bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s);
+  bool run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s);
   bool run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s);
   bool forward(int N, cudaStream_t s);   // in3_ x-channels already packed for N windows -> f3_
   bool ensure_ws(int64_t T);

@@ -38,6 +38,8 @@ SIGNATURES = {
     'vr_separate_wave': (c_i32, [c_vp, c_fp, c_i64, c_i32, c_fp, c_fp, c_vp]),
     'vr_separate_wave_host': (c_i32, [c_vp, c_fp, c_i64, c_i32, c_fp, c_fp, c_vp]),
     'vr_launch_count': (c_i64, [c_vp]),
+    'vr_profile_enable': (c_i32, [c_vp, c_i32]),
+    'vr_profile_read': (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
     'vr_debug_conv': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_i32, c_i32, c_fp, c_vp]),
     'vr_debug_read': (c_i32, [c_vp, ctypes.c_char_p, c_fp, c_i64, ctypes.POINTER(c_i64), c_vp]),
@@ -106,7 +108,8 @@ class Context(object):
             else:
                 arr = arr.astype(np.float32, copy=False)
                 dtype = 0
-            arr = np.ascontiguousarray(arr)
+            if not arr.flags.c_contiguous:
+                arr = arr.copy(order='C')
             shape = (c_i64 * max(1, arr.ndim))(*arr.shape)
             self.check(self.lib.vr_load_tensor(self.handle, key.encode(), dtype, arr.ndim, shape,
                                                arr.ctypes.data_as(c_vp)), 'vr_load_tensor(%s)' % key)

@@ -6,6 +6,7 @@ and the ``predict_mask`` / ``predict`` / ``forward`` calls of lib/nets.py:44-141
 torch layers: the forward runs in libvr_b200.so (hand-written sm_100a kernels) on a CUDA device.
 There is no CPU execution path; calling the model before ``.to(cuda)`` raises.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -40,7 +41,9 @@ class CascadedNet(nn.Module):
             for k, s, kind in self._spec)
         self._device = torch.device('cpu')
         self._ctxs = {}
-        self.conv_mode = 0
+        # 0: tcgen05 tensor-core convolutions where the tile fits (default); 1: CUDA-core kernel everywhere.
+        # VR_CONV_MODE=1 is a validation switch (same device, same library), not a backend.
+        self.conv_mode = int(os.environ.get('VR_CONV_MODE', '0'))
 
     # ---- nn.Module surface used by the reference callers -------------------------------------------
     def state_dict(self, *args, **kwargs):

@@ -144,4 +144,4 @@ def make_state_dict(n_fft=2048, nout=32, nout_lstm=128, seed=0, out_gain=None):
 
 def to_torch_state_dict(sd):
     import torch
-    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+    return {k: torch.from_numpy(np.array(v, copy=True)) for k, v in sd.items()}
