@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference interface (no GPU): geometry, model-load API, sharding, post-process."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import separator_oracle
+
+
+def test_make_padding_matches_oracle():
+    from lib import dataset
+    for width in list(range(1, 600, 7)) + [128, 256, 10336, 103360]:
+        for crop in (256, 192, 128, 512):
+            assert dataset.make_padding(width, crop, 64) == separator_oracle.make_padding(width, crop, 64)
+
+
+def test_window_count_matches_reference_configs():
+    from lib import distributed
+    # 10 s -> 4 windows, 240 s -> 81, 2400 s -> 808
+    assert distributed.window_count(431, 256, 64) == (4, 128)
+    assert distributed.window_count(10336, 256, 64) == (81, 128)
+    assert distributed.window_count(103360, 256, 64) == (808, 128)
+
+
+def test_shard_windows_partition():
+    from lib import distributed
+    for n in (1, 4, 81, 163, 808, 7):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                first, count, per = distributed.shard_windows(n, world, r)
+                assert 0 <= count <= per
+                seen += list(range(first, first + count))
+            assert seen == list(range(n))
+
+
+def test_model_surface_and_strict_loading():
+    from lib import nets, synth
+    m = nets.CascadedNet(2048, 1024, 32, 128)
+    assert (m.offset, m.n_fft, m.hop_length, m.max_bin, m.output_bin) == (64, 2048, 1024, 1024, 1025)
+    assert nets.CascadedASPPNet is nets.CascadedNet
+    sd = synth.to_torch_state_dict(synth.make_state_dict())
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    assert torch.equal(m.state_dict()['out.weight'], sd['out.weight'])
+    assert sum(p.numel() for p in m.parameters()) == 14740882
+    assert m.eval() is m and m.train() is m
+    bad = dict(sd)
+    bad.pop('aux_out.weight')
+    with pytest.raises(RuntimeError, match='Missing key'):
+        m.load_state_dict(bad)
+    bad = dict(sd)
+    bad['out.weight'] = torch.zeros(2, 16, 1, 1)
+    with pytest.raises(RuntimeError, match='size mismatch'):
+        m.load_state_dict(bad)
+    with pytest.raises(RuntimeError, match='no CPU'):
+        m.predict_mask(torch.zeros(1, 2, 1025, 256))
+    with pytest.raises(NotImplementedError):
+        nets.CascadedNet(2048, 1024, 32, 128, is_complex=True)
+
+
+def test_crop_center():
+    from lib import spec_utils
+    a = torch.arange(2 * 3 * 4 * 10.).reshape(2, 3, 4, 10)
+    b = torch.zeros(2, 3, 4, 6)
+    assert spec_utils.crop_center(a, a) is a
+    assert torch.equal(spec_utils.crop_center(a, b), a[:, :, :, 2:8])
+    with pytest.raises(ValueError):
+        spec_utils.crop_center(b, a)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference only exists in the build container')
+def test_merge_artifacts_matches_reference():
+    from oracle import librosa_shim
+    _, _, ref_spec_utils, _ = librosa_shim.import_reference()
+    from lib import spec_utils
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        m = rng.uniform(0.0, 0.04, size=(2, 33, 400)).astype(np.float32)
+        for s, e in ((0, 90), (150, 260), (275, 400))[:1 + trial % 3]:
+            m[:, :, s:e] = rng.uniform(0.06, 1.0, size=(2, 33, e - s))
+        ref = ref_spec_utils.merge_artifacts(m.copy())
+        got = spec_utils.merge_artifacts(m.copy())
+        assert np.allclose(got, ref, atol=1e-7), trial
+    with pytest.raises(ValueError):
+        spec_utils.merge_artifacts(np.ones((2, 3, 100), np.float32), min_range=10, fade_size=32)
+
+
+def _gloo_worker(rank, world, port, n_frames, tmp):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from lib import distributed
+    n_windows, roi = distributed.window_count(n_frames, 256, 64)
+    first, count, per = distributed.shard_windows(n_windows, world, rank)
+    # stand-in for the device result of this rank's windows: frame index encoded in the value
+    full = torch.arange(n_windows * roi, dtype=torch.float32).repeat(2, 5, 1)
+    block = torch.zeros(2, 5, per * roi)
+    lo, hi = distributed.mask_block_frames(first, count, per, roi)
+    block[:, :, :hi - lo] = full[:, :, lo:hi]
+    gathered = distributed.gather_blocks(block, world, rank)
+    if rank == 0:
+        mask = distributed.assemble_mask(gathered, n_frames)
+        torch.save(mask, tmp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    n_frames = 431 + 128 * 3
+    out = str(tmp_path / 'mask.pt')
+    port = 29500 + os.getpid() % 1000
+    mp.spawn(_gloo_worker, args=(2, port, n_frames, out), nprocs=2, join=True)
+    mask = torch.load(out)
+    assert mask.shape == (2, 5, n_frames)
+    assert torch.equal(mask[0, 0], torch.arange(n_frames, dtype=torch.float32))
