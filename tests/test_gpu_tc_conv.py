@@ -24,6 +24,13 @@ TC_CASES = [
     (2, 448, 8, 32, 192, 3, 1, (1, 1), 1),     # dec4 shape class, deep K
     (5, 256, 1, 16, 256, 1, 1, (1, 1), 1),     # ASPP pooled branch: H=1, 8 images per tile, ragged
     (1, 16, 16, 64, 8, 3, 1, (1, 1), 0),       # Cout=8 -> N=16, no activation
+    # row-streaming kernel (3x3, stride 1, W % 128 == 0, H % 8 == 0)
+    (1, 64, 8, 128, 32, 3, 1, (1, 1), 1),
+    (1, 16, 8, 128, 16, 3, 1, (1, 1), 1),      # one 64-channel chunk, mostly TMA zero fill
+    (1, 32, 16, 256, 32, 3, 1, (1, 1), 2),     # two 128-pixel tiles per row
+    (2, 97, 8, 128, 32, 3, 1, (1, 1), 1),      # dec1 class: 97 -> 112 channels, two chunks
+    (1, 192, 16, 128, 64, 3, 1, (1, 1), 1),    # dec2 class: three chunks, two N tiles
+    (3, 2, 24, 256, 8, 3, 1, (1, 1), 0),       # more tiles than one wave per CTA set, Cout 8
 ]
 
 

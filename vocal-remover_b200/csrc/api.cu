@@ -7,6 +7,7 @@
 
 #include "../../include/vr_b200.h"
 #include "engine.h"
+#include "tc_plan.h"
 
 struct vr_ctx {
   vr::Engine* eng;
@@ -173,6 +174,12 @@ int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H
   CHECK_CTX(ctx);
   return done(ctx, ctx->eng->debug_conv(x, N, Cin, H, W, w, bias, Cout, k, stride, dil_h, dil_w, act, use_tc, y,
                                         (cudaStream_t)stream));
+}
+
+int vr_debug_set(int32_t key, int32_t value) {
+  if (key < 0 || key >= 8) return -1;
+  vr::g_tc_debug[key] = value;
+  return 0;
 }
 
 int vr_debug_read(vr_ctx* ctx, const char* what, float* out, int64_t capacity, int64_t* dims, void* stream) {

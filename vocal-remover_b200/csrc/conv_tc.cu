@@ -22,6 +22,8 @@
 #include <tuple>
 
 #include "engine.h"
+#include "tc_common.cuh"
+#include "tc_plan.h"
 
 namespace vr {
 
@@ -42,98 +44,6 @@ struct TcParams {
   const float* bias;
   int tmem_cols;
 };
-
-struct TcConv {
-  int CinPadTC = 0, KB = 0, cchunks = 0, SUBS = 0, taps = 0, Ktot = 0, CoutPadN = 0, BN = 0, n_tiles = 0;
-  bf16* w_planes = nullptr;   // [2][CoutPadN][Ktot]
-  float* bias = nullptr;      // [n_tiles*BN]
-  CUtensorMap map_b;
-  std::map<std::tuple<const void*, const void*, int, int, int, int>, CUtensorMap> map_a;
-};
-
-// ------------------------------------------------------------------------------------------------
-// device helpers (raw PTX; names follow the PTX ISA)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            int c4, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
-      "%6}], [%7];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
-      "[%5];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)
-  uint64_t d = (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
@@ -178,8 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -193,19 +103,23 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int sub0 = it * p.SUBS;
           const int nsub = min(p.SUBS, p.total_sub - sub0);
           const uint32_t full = smem_u32(&bar_full[stage]);
-          mbar_expect_tx(full, (uint32_t)(nsub * (p.a_sub_bytes + p.b_sub_bytes)));
           const uint32_t sbase = smem_base + (uint32_t)(stage * stage_bytes);
+          if (elect_one_sync()) mbar_expect_tx(full, (uint32_t)(nsub * (p.a_sub_bytes + p.b_sub_bytes)));
+          __syncwarp();
           for (int j = 0; j < nsub; ++j) {
             const int sub = sub0 + j;
             const int tap = sub / p.cchunks;
             const int cc = sub - tap * p.cchunks;
             const int kh = tap / p.KW;
             const int kw = tap - kh * p.KW;
-            tma_load_5d(sbase + (uint32_t)(j * p.a_sub_bytes), &tmA, cc * p.KB,
-                        w0 * p.stride - p.pad_w + kw * p.dil_w, h0 * p.stride - p.pad_h + kh * p.dil_h, n0, 0, full);
-            tma_load_3d(sbase + (uint32_t)(b_region + j * p.b_sub_bytes), &tmB, tap * p.CinPadTC + cc * p.KB,
-                        nt * p.BN, 0, full);
+            if (elect_one_sync()) {
+              tma_load_5d(sbase + (uint32_t)(j * p.a_sub_bytes), &tmA, cc * p.KB,
+                          w0 * p.stride - p.pad_w + kw * p.dil_w, h0 * p.stride - p.pad_h + kh * p.dil_h, n0, 0, full);
+              tma_load_3d(sbase + (uint32_t)(b_region + j * p.b_sub_bytes), &tmB, tap * p.CinPadTC + cc * p.KB,
+                          nt * p.BN, 0, full);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -214,8 +128,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -242,19 +156,22 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint64_t da_lo = make_smem_desc(a_lo + ko, p.sbo_bytes, p.layout_type);
               const uint64_t db_hi = make_smem_desc(b_hi + ko, p.sbo_bytes, p.layout_type);
               const uint64_t db_lo = make_smem_desc(b_lo + ko, p.sbo_bytes, p.layout_type);
-              umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-              umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1u);
-              umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1u);
+              if (elect_one_sync()) {
+                umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
+                umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1u);
+                umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1u);
+              }
               accumulate = 1u;
             }
           }
-          umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot once these MMAs have read it
+          __syncwarp();
+          if (elect_one_sync()) umma_commit(smem_u32(&bar_empty[stage]));   // frees the slot once the MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(smem_u32(&bar_tfull[acc]));       // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(smem_u32(&bar_tfull[acc]));       // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -322,11 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -342,14 +257,14 @@ static CUtensorMapSwizzle swizzle_for(int KB) {
   return KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-static uint16_t f2bf(float f) {   // round-to-nearest-even, same as __float2bfloat16_rn for finite values
+uint16_t tc_f2bf(float f) {   // round-to-nearest-even, same as __float2bfloat16_rn for finite values
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
   uint32_t r = 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)((u + r) >> 16);
 }
-static float bf2f(uint16_t h) {
+float tc_bf2f(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
   memcpy(&f, &u, 4);
@@ -388,7 +303,7 @@ bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out) {
   if ((reinterpret_cast<uintptr_t>(in.hi) | reinterpret_cast<uintptr_t>(in.lo)) & 15) return false;
   if (in.C <= 0 || in.N <= 0) return false;
   if ((in.H - 1) / L.stride + 1 != out.H || (in.W - 1) / L.stride + 1 != out.W) return false;
-  return encode_fn() != nullptr;
+  return tc_encode_fn() != nullptr;
 }
 
 bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
@@ -409,8 +324,8 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
     for (int t = 0; t < tc->taps; ++t)
       for (int ci = 0; ci < L.CinPad; ++ci) {
         const float w = L.w_host[((size_t)t * L.CinPad + ci) * L.CoutPad + co];
-        const uint16_t hi = f2bf(w);
-        const uint16_t lo = f2bf(w - bf2f(hi));
+        const uint16_t hi = tc_f2bf(w);
+        const uint16_t lo = tc_f2bf(w - tc_bf2f(hi));
         const size_t k = (size_t)t * tc->CinPadTC + ci;
         planes[(size_t)co * tc->Ktot + k] = hi;
         planes[((size_t)rows + co) * tc->Ktot + k] = lo;
@@ -429,7 +344,7 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
   cudaMemcpy(db, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
   tc->w_planes = (bf16*)dw;
   tc->bias = (float*)db;
-  EncodeTiledFn enc = encode_fn();
+  EncodeTiledFn enc = tc_encode_fn();
   if (!enc) {
     err = "cuTensorMapEncodeTiled is not available from the driver";
     return false;
@@ -445,12 +360,14 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
     err = "cuTensorMapEncodeTiled(weights) failed for " + L.name + " code " + std::to_string((int)r);
     return false;
   }
+  if (!tc_rows_prepare(L, *tc, err, allocs)) return false;
   L.tc = tc;
   return true;
 }
 
 cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err) {
   TcConv& tc = *L.tc;
+  if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err);
   const TileGeom g = tile_geom(out.H, out.W);
   auto key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
   auto it = tc.map_a.find(key);
@@ -466,7 +383,7 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
     cuuint32_t box[5] = {(cuuint32_t)tc.KB, (cuuint32_t)(g.Wt * L.stride), (cuuint32_t)(g.Ht * L.stride),
                          (cuuint32_t)g.Nt, 2};
     cuuint32_t es[5] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1, 1};
-    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in.hi, dims, strides, box, es,
+    CUresult r = tc_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in.hi, dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(tc.KB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

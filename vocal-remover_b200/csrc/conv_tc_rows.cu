@@ -1,0 +1,397 @@
+// Row-streaming tcgen05 convolution: 3x3, stride 1, dilation 1, output width a multiple of 128.
+//
+// The generic kernel (conv_tc.cu) re-fetches every input pixel from L2 once per tap (9x) and is bound
+// by L2->SM bandwidth on the wide, shallow layers (enc1, enc2.conv2, dec2, dec1 of every BaseNet:
+// 69 % of the convolution time in profiles/r01_launches_bench30s_v1_direct.csv).  Here one CTA owns a
+// block of R=8 output rows x 128 pixels x BN couts with R accumulators resident in TMEM, and streams
+// the R+2 input rows it needs through shared memory ONCE per 64-channel chunk:
+//   * each input row (130 pixels incl. the +-1 halo, 64 channels, hi and lo plane) is one pair of TMA
+//     loads; out-of-image rows / columns are zero-filled by TMA = the conv padding;
+//   * a row feeds up to three output rows (kh = 0,1,2) and, for each, the three kw taps are the SAME
+//     shared-memory tile read through UMMA descriptors whose start address is shifted by kw pixels
+//     (+ kw * 128 B) - no data movement per tap.  Measured on B200 (tests/diag_rows.py): the 128B swizzle is
+//     applied to the absolute shared-memory address, so the shifted start needs NO matrix-base-offset
+//     (setting the field to (addr>>7)&7 produces garbage);
+//   * the weights of the three kh taps are STACKED along the MMA N dimension ([kh=2 | kh=1 | kh=0] x BN couts)
+//     and the R accumulators sit in adjacent TMEM columns, so ONE tcgen05.mma of N = 3*BN adds an input
+//     row's contribution to output rows r-2, r-1 and r at once: 3x fewer, 3x larger MMA instructions (with
+//     N = 16/32 the single issuing thread, not the tensor pipe, was the limit);
+//   * the 9-tap weight slab of the chunk (3 kw x [3*BN] x 64, hi+lo) is double-buffered in shared memory.
+// L2->SM traffic per output pixel drops from 9 to (R+2)/R = 1.25 operand fetches.
+#include <stdio.h>
+
+#include "engine.h"
+#include "tc_common.cuh"
+#include "tc_plan.h"
+
+namespace vr {
+
+static constexpr int kRowsThreads = 192;
+static constexpr int kR = 8;                       // output rows per CTA tile
+static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
+static constexpr int kAPlane = 17 * 1024;          // 130 * 128 B = 16640, padded to a 1 KiB multiple
+static constexpr int kASlot = 2 * kAPlane;         // hi + lo
+static constexpr int kASlots = 2;
+
+struct RowsParams {
+  int N, H, W, tiles_w, tiles_h, n_tiles, total_tiles;
+  int chunks, CinPadR, BN, Cout, act;
+  int b_kw_bytes, b_buf_bytes;
+  uint32_t idesc0;   // instruction descriptor without the N field
+  bf16* out_hi;
+  bf16* out_lo;
+  int64_t osn, osh;
+  int osw;
+  const float* bias;
+  int tmem_cols;
+  int bo_mode;
+};
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+    conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_afull[kASlots];
+  __shared__ __align__(8) uint64_t bar_aempty[kASlots];
+  __shared__ __align__(8) uint64_t bar_bfull[2];
+  __shared__ __align__(8) uint64_t bar_bempty[2];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + (uint32_t)(kASlots * kASlot);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < kASlots; ++s) {
+      mbar_init(smem_u32(&bar_afull[s]), 1);
+      mbar_init(smem_u32(&bar_aempty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_bfull[s]), 1);
+      mbar_init(smem_u32(&bar_bempty[s]), 1);
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * 128;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * kR;
+        const int n = mt / p.tiles_h;
+        for (int cc = 0; cc < p.chunks; ++cc) {
+          mbar_wait(smem_u32(&bar_bempty[bs]), bph ^ 1u);
+          const uint32_t bfull = smem_u32(&bar_bfull[bs]);
+          const uint32_t bdst = b_base + (uint32_t)(bs * p.b_buf_bytes);
+          if (elect_one_sync()) {
+            mbar_expect_tx(bfull, (uint32_t)(3 * p.b_kw_bytes));
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              tma_load_3d(bdst + (uint32_t)(kw * p.b_kw_bytes), &tmB, kw * p.CinPadR + cc * 64, nt * 3 * p.BN, 0,
+                          bfull);
+          }
+          __syncwarp();
+          if (++bs == 2) {
+            bs = 0;
+            bph ^= 1u;
+          }
+          for (int r = 0; r < kR + 2; ++r) {
+            mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
+            const uint32_t afull = smem_u32(&bar_afull[as]);
+            const uint32_t adst = a_base + (uint32_t)(as * kASlot);
+            if (elect_one_sync()) {
+              mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * 128));
+              tma_load_5d(adst, &tmA, cc * 64, w0 - 1, h0 - 1 + r, n, 0, afull);
+              tma_load_5d(adst + (uint32_t)kAPlane, &tmA, cc * 64, w0 - 1, h0 - 1 + r, n, 1, afull);
+            }
+            __syncwarp();
+            if (++as == kASlots) {
+              as = 0;
+              aph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+    {
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      const uint32_t b3_plane = (uint32_t)(3 * p.BN * 128);   // hi -> lo plane inside one kw slab
+      const uint32_t dhi = desc_hi(1024, 2);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_set = tmem_base + (uint32_t)(acc * kR * p.BN);
+        for (int cc = 0; cc < p.chunks; ++cc) {
+          mbar_wait(smem_u32(&bar_bfull[bs]), bph);
+          const uint32_t bsrc = b_base + (uint32_t)(bs * p.b_buf_bytes);
+          for (int r = 0; r < kR + 2; ++r) {
+            mbar_wait(smem_u32(&bar_afull[as]), aph);
+            tc_fence_after();
+            const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * kASlot));
+            const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * kASlot + kAPlane));
+            // input row r feeds output rows o = r-kh; accumulators o_lo..o_hi are adjacent TMEM column blocks
+            const int o_lo = r - 2 < 0 ? 0 : r - 2;
+            const int o_hi = r > kR - 1 ? kR - 1 : r;
+            const int cnt = o_hi - o_lo + 1;
+            const uint32_t d_tmem = d_set + (uint32_t)(o_lo * p.BN);
+            // weight rows are stacked [kh=2 | kh=1 | kh=0]; block of accumulator o_lo is kh = r - o_lo
+            const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN * 128);
+            const uint32_t idesc_all = p.idesc0 | ((uint32_t)((cnt * p.BN) >> 3) << 17);
+            const bool fresh = cc == 0 && r <= kR - 1;   // accumulator r receives its first product now
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t bk_hi = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b_row0);
+              const uint32_t bk_lo = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b3_plane + b_row0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t ao = (uint32_t)((kw * 128 + ks * 32) >> 4);
+                const uint32_t ko = (uint32_t)((ks * 32) >> 4);
+                if (kw == 0 && ks == 0 && fresh) {
+                  // first touch of accumulator r must overwrite: split the stacked MMA once
+                  const uint32_t n_old = (uint32_t)((cnt - 1) * p.BN);
+                  const uint32_t idesc_old = p.idesc0 | ((n_old >> 3) << 17);
+                  const uint32_t idesc_new = p.idesc0 | ((uint32_t)(p.BN >> 3) << 17);
+                  const uint32_t bn_off = (uint32_t)(((cnt - 1) * p.BN * 128) >> 4);
+                  if (elect_one_sync()) {
+                    if (cnt > 1) {
+                      umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_old, 1u);
+                      umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_old, 1u);
+                      umma_bf16_w(d_tmem, a_hi + ao, bk_lo + ko, dhi, idesc_old, 1u);
+                    }
+                    umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_hi + ko + bn_off, dhi, idesc_new, 0u);
+                    umma_bf16_w(d_tmem + n_old, a_lo + ao, bk_hi + ko + bn_off, dhi, idesc_new, 1u);
+                    umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_lo + ko + bn_off, dhi, idesc_new, 1u);
+                  }
+                } else {
+                  if (elect_one_sync()) {
+                    umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_all, 1u);
+                    umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_all, 1u);
+                    umma_bf16_w(d_tmem, a_hi + ao, bk_lo + ko, dhi, idesc_all, 1u);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (elect_one_sync()) umma_commit(smem_u32(&bar_aempty[as]));
+            if (++as == kASlots) {
+              as = 0;
+              aph ^= 1u;
+            }
+          }
+          if (elect_one_sync()) umma_commit(smem_u32(&bar_bempty[bs]));
+          if (++bs == 2) {
+            bs = 0;
+            bph ^= 1u;
+          }
+        }
+        if (elect_one_sync()) umma_commit(smem_u32(&bar_tfull[acc]));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int px = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int w0 = (mt % p.tiles_w) * 128;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * kR;
+      const int n = mt / p.tiles_h;
+      mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_set = tmem_base + (uint32_t)(acc * kR * p.BN) + ((uint32_t)(q * 32) << 16);
+      for (int orow = 0; orow < kR; ++orow) {
+        const int64_t obase = (int64_t)n * p.osn + (int64_t)(h0 + orow) * p.osh + (int64_t)(w0 + px) * p.osw;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(t_set + (uint32_t)(orow * p.BN + c0), v);
+          if (orow == kR - 1 && c0 + 16 >= p.BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+          }
+#pragma unroll
+          for (int g = 0; g < 16; g += 8) {
+            const int co = nt * p.BN + c0 + g;
+            const int cnt = min(8, p.Cout - co);
+            if (cnt > 0) {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = act_apply(v[g + i] + __ldg(p.bias + co + i), p.act);
+              store_split(p.out_hi + obase + co, p.out_lo + obase + co, y, cnt);
+            }
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<void*>& allocs) {
+  TcRowsPlan& R = tc.rows;
+  R.ok = false;
+  if (L.k != 3 || L.stride != 1 || L.dil_h != 1 || L.dil_w != 1) return true;
+  const int cout16 = round_up(L.Cout, 16);
+  R.BN = cout16 == 16 ? 16 : 32;
+  R.n_tiles = ceil_div(cout16, R.BN);
+  R.CinPadR = round_up(L.CinPad, 64);
+  R.chunks = R.CinPadR / 64;
+  // B[plane][nt*3*BN + (2-kh)*BN + co][kw*CinPadR + ci]: the three kh taps stacked along the MMA N dimension
+  const int rows = R.n_tiles * R.BN;
+  const int brows = 3 * rows;
+  const int Ktot = 3 * R.CinPadR;
+  std::vector<uint16_t> planes((size_t)2 * brows * Ktot, 0);
+  for (int co = 0; co < L.Cout; ++co) {
+    const int nt = co / R.BN, col = co % R.BN;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ci = 0; ci < L.CinPad; ++ci) {
+          const float w = L.w_host[((size_t)(kh * 3 + kw) * L.CinPad + ci) * L.CoutPad + co];
+          const uint16_t hi = tc_f2bf(w);
+          const uint16_t lo = tc_f2bf(w - tc_bf2f(hi));
+          const size_t row = (size_t)nt * 3 * R.BN + (size_t)(2 - kh) * R.BN + col;
+          const size_t k = (size_t)kw * R.CinPadR + ci;
+          planes[row * Ktot + k] = hi;
+          planes[((size_t)brows + row) * Ktot + k] = lo;
+        }
+  }
+  std::vector<float> bias((size_t)rows, 0.f);
+  for (int co = 0; co < L.Cout; ++co) bias[(size_t)co] = L.bias_host[(size_t)co];
+  void* dw = nullptr;
+  void* db = nullptr;
+  if (cudaMalloc(&dw, planes.size() * 2) != cudaSuccess || cudaMalloc(&db, bias.size() * 4) != cudaSuccess) {
+    err = "cudaMalloc failed while packing row-kernel weights for " + L.name;
+    return false;
+  }
+  allocs.push_back(dw);
+  allocs.push_back(db);
+  cudaMemcpy(dw, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+  R.w_planes = (bf16*)dw;
+  R.bias = (float*)db;
+  cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)brows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)Ktot * 2, (cuuint64_t)brows * Ktot * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)(3 * R.BN), 2};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = tc_encode_fn()(&R.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dw, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    err = "cuTensorMapEncodeTiled(row-kernel weights) failed for " + L.name + " code " + std::to_string((int)r);
+    return false;
+  }
+  R.ok = true;
+  return true;
+}
+
+bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out) {
+  if (!tc.rows.ok || g_tc_debug[1]) return false;
+  if (L.k != 3 || L.stride != 1 || L.dil_h != 1 || L.dil_w != 1) return false;
+  if (out.W % 128 || out.H % kR || in.H != out.H || in.W != out.W) return false;
+  if (in.sw % 8 || in.sh % 8 || in.sn % 8) return false;
+  if ((reinterpret_cast<uintptr_t>(in.hi) | reinterpret_cast<uintptr_t>(in.lo)) & 15) return false;
+  return true;
+}
+
+cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
+                           std::string& err) {
+  TcRowsPlan& R = tc.rows;
+  ViewKey key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
+  auto it = R.map_a.find(key);
+  if (it == R.map_a.end()) {
+    CUtensorMap m;
+    cuuint64_t dims[5] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N, 2};
+    const int64_t plane = (const char*)in.lo - (const char*)in.hi;
+    if (plane <= 0 || plane % 16) {
+      err = "tc_rows_launch: hi/lo planes must be 16-byte aligned with lo after hi";
+      return cudaErrorInvalidValue;
+    }
+    cuuint64_t strides[4] = {(cuuint64_t)in.sw * 2, (cuuint64_t)in.sh * 2, (cuuint64_t)in.sn * 2, (cuuint64_t)plane};
+    cuuint32_t box[5] = {64, (cuuint32_t)kRowPx, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = tc_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in.hi, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      err = "cuTensorMapEncodeTiled(row-kernel activations) failed for " + L.name + " code " + std::to_string((int)r);
+      return cudaErrorInvalidValue;
+    }
+    it = R.map_a.emplace(key, m).first;
+  }
+  RowsParams p;
+  p.N = out.N; p.H = out.H; p.W = out.W;
+  p.tiles_w = out.W / 128; p.tiles_h = out.H / kR; p.n_tiles = R.n_tiles;
+  p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
+  p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.BN = R.BN; p.Cout = L.Cout; p.act = L.act;
+  p.b_kw_bytes = 2 * 3 * R.BN * 128;
+  p.b_buf_bytes = 3 * p.b_kw_bytes;
+  p.idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+  p.out_hi = out.hi; p.out_lo = out.lo;
+  p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
+  p.bias = R.bias;
+  p.tmem_cols = 2 * kR * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
+  p.bo_mode = g_tc_debug[0];
+  const int dyn = kASlots * kASlot + 2 * p.b_buf_bytes + 1024;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, p);
+  return cudaGetLastError();
+}
+
+}  // namespace vr

@@ -1,0 +1,46 @@
+// Host-side plan of one convolution layer for the tcgen05 kernels (conv_tc.cu, conv_tc_rows.cu).
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "engine.h"
+
+namespace vr {
+
+typedef std::tuple<const void*, const void*, int, int, int, int> ViewKey;
+
+struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 128 == 0 (conv_tc_rows.cu)
+  bool ok = false;
+  int CinPadR = 0, chunks = 0, BN = 0, n_tiles = 0;
+  bf16* w_planes = nullptr;   // [2][n_tiles*BN][9*CinPadR]
+  float* bias = nullptr;      // [n_tiles*BN]
+  CUtensorMap map_b;
+  std::map<ViewKey, CUtensorMap> map_a;
+};
+
+struct TcConv {
+  int CinPadTC = 0, KB = 0, cchunks = 0, SUBS = 0, taps = 0, Ktot = 0, CoutPadN = 0, BN = 0, n_tiles = 0;
+  bf16* w_planes = nullptr;   // [2][CoutPadN][Ktot]
+  float* bias = nullptr;      // [n_tiles*BN]
+  CUtensorMap map_b;
+  std::map<ViewKey, CUtensorMap> map_a;
+  TcRowsPlan rows;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tc_encode_fn();
+uint16_t tc_f2bf(float f);
+float tc_bf2f(uint16_t h);
+
+// conv_tc_rows.cu
+bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<void*>& allocs);
+bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
+cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
+                           std::string& err);
+extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable the rows kernel
+
+}  // namespace vr

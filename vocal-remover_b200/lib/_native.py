@@ -42,6 +42,7 @@ SIGNATURES = {
     'vr_profile_read': (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
     'vr_debug_conv': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_i32, c_i32, c_fp, c_vp]),
+    'vr_debug_set': (c_i32, [c_i32, c_i32]),
     'vr_debug_read': (c_i32, [c_vp, ctypes.c_char_p, c_fp, c_i64, ctypes.POINTER(c_i64), c_vp]),
 }
 
