@@ -55,40 +55,80 @@ __device__ __forceinline__ float join_bf16(bf16 hi, bf16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);
 }
 
-// 8 consecutive bf16 (16 bytes) <-> 8 floats
-struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+// 8 consecutive bf16 (16 bytes) <-> 8 floats.  All 16-byte accesses go through uint4 so that they compile to
+// LDG.E.128 / STG.E.128 (a struct of __nv_bfloat162 members is copied member-wise as 4-byte accesses).
+typedef uint4 bf16x8;
 
-__device__ __forceinline__ void load8(const bf16* hi, const bf16* lo, float* x) {
-  bf16x8 a = *reinterpret_cast<const bf16x8*>(hi);
-  bf16x8 b = *reinterpret_cast<const bf16x8*>(lo);
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  // bf16 -> fp32 is a 16-bit shift
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ bf16x8 ld128(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st128(bf16* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ void unpack8(const bf16x8& a, const bf16x8& b, float* x) {
+  const uint32_t ua[4] = {a.x, a.y, a.z, a.w};
+  const uint32_t ub[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 fa = __bfloat1622float2(a.v[i]);
-    float2 fb = __bfloat1622float2(b.v[i]);
+    float2 fa = bf2_to_f2(ua[i]);
+    float2 fb = bf2_to_f2(ub[i]);
     x[2 * i] = fa.x + fb.x;
     x[2 * i + 1] = fa.y + fb.y;
   }
 }
 
-__device__ __forceinline__ void split8(const float* x, bf16x8& h, bf16x8& l) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-    float2 hf = __bfloat1622float2(hh);
-    h.v[i] = hh;
-    l.v[i] = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
-  }
+__device__ __forceinline__ void load8(const bf16* hi, const bf16* lo, float* x) {
+  unpack8(ld128(hi), ld128(lo), x);
 }
 
-// Store `cnt` consecutive channels (fp32 values) as split-bf16 at element offset `off` of a pixel.
+__device__ __forceinline__ void split8(const float* x, bf16x8& h, bf16x8& l) {
+  uint32_t uh[4], ul[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uh[i] = f2_to_bf2(x[2 * i], x[2 * i + 1]);
+    float2 hf = bf2_to_f2(uh[i]);
+    ul[i] = f2_to_bf2(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+  }
+  h = make_uint4(uh[0], uh[1], uh[2], uh[3]);
+  l = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+}
+
+// 32-byte (16-channel) store: one full sector per lane (STG.E.256 on sm_100a)
+__device__ __forceinline__ void st256(bf16* p, const bf16x8& a, const bf16x8& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// Store `cnt` consecutive channels (fp32 values) of one pixel as split-bf16.
 __device__ __forceinline__ void store_split(bf16* hi, bf16* lo, const float* x, int cnt) {
   if (cnt == 8 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
     bf16x8 h, l;
     split8(x, h, l);
-    *reinterpret_cast<bf16x8*>(hi) = h;
-    *reinterpret_cast<bf16x8*>(lo) = l;
+    st128(hi, h);
+    st128(lo, l);
   } else {
     for (int i = 0; i < cnt; ++i) split_bf16(x[i], hi[i], lo[i]);
+  }
+}
+
+// 16 consecutive channels; uses full-sector 32-byte stores when the destination allows it
+__device__ __forceinline__ void store_split16(bf16* hi, bf16* lo, const float* x, int cnt) {
+  if (cnt == 16 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 31) == 0) {
+    bf16x8 h0, l0, h1, l1;
+    split8(x, h0, l0);
+    split8(x + 8, h1, l1);
+    st256(hi, h0, h1);
+    st256(lo, l0, l1);
+  } else {
+    store_split(hi, lo, x, cnt < 8 ? cnt : 8);
+    if (cnt > 8) store_split(hi + 8, lo + 8, x + 8, cnt - 8);
   }
 }
 

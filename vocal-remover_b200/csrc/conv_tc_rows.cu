@@ -244,15 +244,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
           }
-#pragma unroll
-          for (int g = 0; g < 16; g += 8) {
-            const int co = nt * p.BN + c0 + g;
-            const int cnt = min(8, p.Cout - co);
+{
+            const int co = nt * p.BN + c0;
+            const int cnt = min(16, p.Cout - co);
             if (cnt > 0) {
-              float y[8];
+              float y[16];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = act_apply(v[g + i] + __ldg(p.bias + co + i), p.act);
-              store_split(p.out_hi + obase + co, p.out_lo + obase + co, y, cnt);
+              for (int i = 0; i < 16; ++i) y[i] = act_apply(v[i] + __ldg(p.bias + co + i), p.act);
+              store_split16(p.out_hi + obase + co, p.out_lo + obase + co, y, cnt);
             }
           }
         }

@@ -111,8 +111,8 @@ __global__ void upsample2x_kernel(ActView in, ActView out) {
   int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * 8;
   bf16x8 h, l;
   split8(y, h, l);
-  *reinterpret_cast<bf16x8*>(out.hi + oo) = h;
-  *reinterpret_cast<bf16x8*>(out.lo + oo) = l;
+  st128(out.hi + oo, h);
+  st128(out.lo + oo, l);
 }
 
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
@@ -148,8 +148,8 @@ __global__ void pool_freq_mean_kernel(ActView in, ActView out) {
   int64_t oo = (int64_t)n * out.sn + (int64_t)w * out.sw + ck * 8;
   bf16x8 hh, ll;
   split8(acc, hh, ll);
-  *reinterpret_cast<bf16x8*>(out.hi + oo) = hh;
-  *reinterpret_cast<bf16x8*>(out.lo + oo) = ll;
+  st128(out.hi + oo, hh);
+  st128(out.lo + oo, ll);
 }
 
 cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream) {
@@ -172,8 +172,8 @@ __global__ void broadcast_rows_kernel(ActView in, ActView out) {
   int n = (int)(r / out.H);
   int64_t oi = (int64_t)n * in.sn + (int64_t)w * in.sw + ck * 8;
   int64_t oo = (int64_t)n * out.sn + (int64_t)h * out.sh + (int64_t)w * out.sw + ck * 8;
-  *reinterpret_cast<bf16x8*>(out.hi + oo) = *reinterpret_cast<const bf16x8*>(in.hi + oi);
-  *reinterpret_cast<bf16x8*>(out.lo + oo) = *reinterpret_cast<const bf16x8*>(in.lo + oi);
+  st128(out.hi + oo, ld128(in.hi + oi));
+  st128(out.lo + oo, ld128(in.lo + oi));
 }
 
 cudaError_t launch_broadcast_rows(ActView in, ActView out, cudaStream_t stream) {

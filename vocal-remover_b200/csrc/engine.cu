@@ -184,8 +184,9 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     err = "unsupported geometry: band height and cropsize must be multiples of 16 and nout a multiple of 16";
     return false;
   }
-  const int c1 = round_up(3 * n + 8, 16);
-  P.e1_off = 2 * n + 8;
+  // lstm channel + 15 zero channels keep every slice 32-byte aligned (full-sector 256-bit epilogue stores)
+  const int c1 = round_up(3 * n + 16, 16);
+  P.e1_off = 2 * n + 16;
   P.cat1 = make_buffer(Nb, H, W, c1);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
@@ -201,7 +202,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.ao = make_buffer(Nb, H / 16, W / 16, 8 * n);
   P.d4 = make_buffer(Nb, H / 8, W / 8, 6 * n);
   P.d3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
-  P.d2 = make_buffer(Nb, H / 2, W / 2, 2 * n + 8);
+  P.d2 = make_buffer(Nb, H / 2, W / 2, 2 * n + 16);
   if (!P.d2.hi || !P.cat1.hi) return false;
 
   if (!make_conv(P.enc1, prefix + ".enc1", in_perm, cin_pad, 3, 1, 1, 1, ACT_RELU)) return false;
@@ -232,7 +233,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     return false;
   {
     // dec1 input in the reference: cat[ up(cat[h (2n), lstm (1)]) , e1 (n) ]  (lib/nets.py:38-39, layers.py:52-56)
-    // packed as [ up(h) 2n | up(lstm) 1 | 7 zeros | e1 n | zeros ]
+    // packed as [ up(h) 2n | up(lstm) 1 | 15 zeros | e1 n | zeros ]
     std::vector<int> perm((size_t)c1, -1);
     for (int i = 0; i < 2 * n + 1; ++i) perm[(size_t)i] = i;
     for (int i = 0; i < n; ++i) perm[(size_t)(P.e1_off + i)] = 2 * n + 1 + i;
@@ -495,7 +496,7 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
           "lstm dense"))
     return false;
   // dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
-  if (!ck(launch_upsample2x(P.d2.all(N), P.cat1.view(N, 0, H, 0, 2 * n + 8), s), "up1")) return false;
+  if (!ck(launch_upsample2x(P.d2.all(N), P.cat1.view(N, 0, H, 0, 2 * n + 16), s), "up1")) return false;
   return run_conv(P.dec[3], P.cat1.all(N), out, s);
 }
 
