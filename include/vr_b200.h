@@ -105,6 +105,15 @@ VR_API int vr_separate_wave(vr_ctx* ctx, const float* wave, int64_t L, int32_t t
 VR_API int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_t tta, float* inst_host,
                           float* voc_host, void* stream);
 
+/* Multi-GPU mask exchange over NVLink peer memory (one process per GPU).  The owner (rank 0) allocates the
+ * whole-track mask with vr_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it
+ * with vr_shared_open and passes the mapped pointer as `mask` to vr_separate_windows, so the mask epilogue
+ * kernel itself stores its shard into rank 0's HBM - the "gather" of Separator._separate's concatenate
+ * (inference.py:63-66) fused into the producing kernel.  vr_shared_close unmaps (owner=0) or frees (owner=1). */
+VR_API int vr_shared_alloc(vr_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* handle64);
+VR_API int vr_shared_open(vr_ctx* ctx, const unsigned char* handle64, void** dev_ptr);
+VR_API int vr_shared_close(vr_ctx* ctx, void* dev_ptr, int32_t owner);
+
 /* Number of kernels launched by this context so far (bench.py 'gpu_launches').                           */
 VR_API int64_t vr_launch_count(const vr_ctx* ctx);
 

@@ -155,6 +155,47 @@ int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_
   return done(ctx, ctx->eng->separate_wave_host(wave_host, L, tta, inst_host, voc_host, (cudaStream_t)stream));
 }
 
+int vr_shared_alloc(vr_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  CHECK_CTX(ctx);
+  if (!dev_ptr || !handle64 || bytes <= 0) return fail(ctx, "vr_shared_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaSetDevice(ctx->eng->cfg().device);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) return fail(ctx, std::string("vr_shared_alloc: cudaMalloc: ") + cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(ctx, std::string("vr_shared_alloc: cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int vr_shared_open(vr_ctx* ctx, const unsigned char* handle64, void** dev_ptr) {
+  CHECK_CTX(ctx);
+  if (!dev_ptr || !handle64) return fail(ctx, "vr_shared_open: bad arguments");
+  cudaSetDevice(ctx->eng->cfg().device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(ctx, std::string("vr_shared_open: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  *dev_ptr = p;
+  return 0;
+}
+
+int vr_shared_close(vr_ctx* ctx, void* dev_ptr, int32_t owner) {
+  CHECK_CTX(ctx);
+  if (!dev_ptr) return 0;
+  cudaSetDevice(ctx->eng->cfg().device);
+  cudaError_t e = owner ? cudaFree(dev_ptr) : cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) return fail(ctx, std::string("vr_shared_close: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 int64_t vr_launch_count(const vr_ctx* ctx) { return ctx && ctx->eng ? ctx->eng->launches : 0; }
 
 int vr_profile_enable(vr_ctx* ctx, int32_t on) {

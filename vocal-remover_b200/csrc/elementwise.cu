@@ -76,39 +76,36 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// One thread per (output pixel, 8-channel chunk).  Source index and weights follow ATen's
-// upsample_bilinear2d with align_corners=True: scale = (in-1)/(out-1) in fp32, src = scale*dst.
-__global__ void upsample2x_kernel(ActView in, ActView out) {
-  const int chunks = in.C >> 3;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = (int64_t)out.N * out.H * out.W * chunks;
-  if (idx >= total) return;
-  int ck = (int)(idx % chunks);
-  int64_t r = idx / chunks;
-  int wo = (int)(r % out.W);
-  r /= out.W;
-  int ho = (int)(r % out.H);
-  int n = (int)(r / out.H);
-  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
-  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
-  float fy = sh * ho, fx = sw * wo;
-  int y0 = (int)fy, x0 = (int)fx;
-  int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
-  float ly = fy - y0, lx = fx - x0;
-  float hy = 1.f - ly, hx = 1.f - lx;
+// One thread per (output pixel, 8-channel chunk); grid.y = (image, output row) so all per-thread index math is
+// 32-bit with one division.  Source index and weights follow ATen's upsample_bilinear2d with
+// align_corners=True: scale = (in-1)/(out-1) in fp32, src = scale*dst.
+__global__ void __launch_bounds__(256) upsample2x_kernel(ActView in, ActView out, int chunks, float sh, float sw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= out.W * chunks) return;
+  const int wo = idx / chunks;
+  const int ck = idx - wo * chunks;
+  const int n = blockIdx.y / out.H;
+  const int ho = blockIdx.y - n * out.H;
+  const float fy = sh * ho, fx = sw * wo;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
   const int64_t base = (int64_t)n * in.sn + ck * 8;
+  const int64_t r0 = base + (int64_t)y0 * in.sh, r1 = base + (int64_t)y1 * in.sh;
+  const int c0 = x0 * in.sw, c1 = x1 * in.sw;
+  const bf16x8 ah = ld128(in.hi + r0 + c0), al = ld128(in.lo + r0 + c0);
+  const bf16x8 bh = ld128(in.hi + r0 + c1), bl = ld128(in.lo + r0 + c1);
+  const bf16x8 ch = ld128(in.hi + r1 + c0), cl = ld128(in.lo + r1 + c0);
+  const bf16x8 dh = ld128(in.hi + r1 + c1), dl = ld128(in.lo + r1 + c1);
   float a[8], b[8], c[8], d[8], y[8];
-  int64_t o00 = base + (int64_t)y0 * in.sh + (int64_t)x0 * in.sw;
-  int64_t o01 = base + (int64_t)y0 * in.sh + (int64_t)x1 * in.sw;
-  int64_t o10 = base + (int64_t)y1 * in.sh + (int64_t)x0 * in.sw;
-  int64_t o11 = base + (int64_t)y1 * in.sh + (int64_t)x1 * in.sw;
-  load8(in.hi + o00, in.lo + o00, a);
-  load8(in.hi + o01, in.lo + o01, b);
-  load8(in.hi + o10, in.lo + o10, c);
-  load8(in.hi + o11, in.lo + o11, d);
+  unpack8(ah, al, a);
+  unpack8(bh, bl, b);
+  unpack8(ch, cl, c);
+  unpack8(dh, dl, d);
 #pragma unroll
   for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-  int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * 8;
+  const int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * 8;
   bf16x8 h, l;
   split8(y, h, l);
   st128(out.hi + oo, h);
@@ -116,9 +113,12 @@ __global__ void upsample2x_kernel(ActView in, ActView out) {
 }
 
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
-  int64_t total = (int64_t)out.N * out.H * out.W * (in.C >> 3);
-  if (total == 0) return cudaSuccess;
-  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+  const int chunks = in.C >> 3;
+  if ((int64_t)out.N * out.H * out.W * chunks == 0) return cudaSuccess;
+  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
+  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  dim3 grid((unsigned)ceil_div(out.W * chunks, 256), (unsigned)(out.N * out.H));
+  upsample2x_kernel<<<grid, 256, 0, stream>>>(in, out, chunks, sh, sw);
   return cudaGetLastError();
 }
 

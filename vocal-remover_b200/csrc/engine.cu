@@ -64,6 +64,9 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
   if (!twiddle_ || !window_ || !ws_norm_ || !ws_lex_) return;
   cudaMemcpy(twiddle_, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
   cudaMemcpy(window_, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice);
+  cudaStreamCreateWithFlags(&s_hi_, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming);
 }
 
 Engine::~Engine() {
@@ -73,6 +76,10 @@ Engine::~Engine() {
   if (ws_mask_) cudaFree(ws_mask_);
   if (ws_frames_) cudaFree(ws_frames_);
   if (ws_wave_) cudaFree(ws_wave_);
+  profile_enable(false);
+  if (s_hi_) cudaStreamDestroy(s_hi_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 bool Engine::load_tensor(const char* name, int dtype, int ndim, const int64_t* shape, const void* data) {
@@ -505,18 +512,28 @@ bool Engine::forward(int N, cudaStream_t s) {
   const int nout = cfg_.nout, a1 = nout / 4, a2 = nout / 2;
   const int c0_1 = pos_x_ / 16 * 16, c0_2 = pos_aux1_ / 16 * 16;
   last_n_ = N;
-  // stage 1 (lib/nets.py:91-93)
+  // Stages 1 and 2 (lib/nets.py:91-99): the low-band chain (stg1_low -> bridge -> stg2_low -> bridge) and the
+  // high-band chain (stg1_high -> stg2_high) only meet at stage 3, so they run on two streams.
+  const bool two = s_hi_ != nullptr && !profiling_;
+  cudaStream_t sh = two ? s_hi_ : s;
+  if (two) {
+    if (!ck(cudaEventRecord(ev_fork_, s), "fork") || !ck(cudaStreamWaitEvent(s_hi_, ev_fork_, 0), "fork wait"))
+      return false;
+  }
+  if (!run_basenet(nets_[1], in3_.view(N, Hb, Hb, c0_1, nets_[1].enc1.CinPad), in3_.view(N, Hb, Hb, pos_aux1_, a1), N,
+                   sh))
+    return false;
+  if (!run_basenet(nets_[3], in3_.view(N, Hb, Hb, c0_2, nets_[3].enc1.CinPad), in3_.view(N, Hb, Hb, pos_aux2_, a2), N,
+                   sh))
+    return false;
   if (!run_basenet(nets_[0], in3_.view(N, 0, Hb, c0_1, nets_[0].enc1.CinPad), o1_.all(N), N, s)) return false;
   if (!run_conv(bridge1_, o1_.all(N), in3_.view(N, 0, Hb, pos_aux1_, a1), s)) return false;
-  if (!run_basenet(nets_[1], in3_.view(N, Hb, Hb, c0_1, nets_[1].enc1.CinPad), in3_.view(N, Hb, Hb, pos_aux1_, a1), N,
-                   s))
-    return false;
-  // stage 2 (lib/nets.py:95-99)
   if (!run_basenet(nets_[2], in3_.view(N, 0, Hb, c0_2, nets_[2].enc1.CinPad), o2_.all(N), N, s)) return false;
   if (!run_conv(bridge2_, o2_.all(N), in3_.view(N, 0, Hb, pos_aux2_, a2), s)) return false;
-  if (!run_basenet(nets_[3], in3_.view(N, Hb, Hb, c0_2, nets_[3].enc1.CinPad), in3_.view(N, Hb, Hb, pos_aux2_, a2), N,
-                   s))
-    return false;
+  if (two) {
+    if (!ck(cudaEventRecord(ev_join_, s_hi_), "join") || !ck(cudaStreamWaitEvent(s, ev_join_, 0), "join wait"))
+      return false;
+  }
   // stage 3 (lib/nets.py:101-102)
   return run_basenet(nets_[4], in3_.all(N), f3_.all(N), N, s);
 }

@@ -140,6 +140,11 @@ class Engine {
   float* ws_norm_ = nullptr;            // [4] floats: absmax, lexmax-abs
   unsigned long long* ws_lex_ = nullptr;
 
+  // the high-band BaseNets of stages 1-2 run on their own stream next to the low-band chain (independent until
+  // stage 3, lib/nets.py:88-99); disabled while per-kernel profiling is on so event timings stay per-kernel
+  cudaStream_t s_hi_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+
   float2* twiddle_ = nullptr;
   float* window_ = nullptr;
 
