@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[256];   // folded-BN bias of every N tile, staged once (a global load per use stalled the epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const float slope = p.act == ACT_RELU ? 0.f : p.act == ACT_LEAKY ? 0.01f : 1.f;
     const int dw = row % p.Wt;
     const int dh = (row / p.Wt) % p.Ht;
     const int dn = row / (p.Wt * p.Ht);
@@ -199,26 +202,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        if (c0 + 16 >= p.BN) {   // all of this warp's TMEM reads are done: hand the accumulator back
+      int c0 = 0;
+      for (; c0 + 32 <= p.BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        if (c0 + 32 >= p.BN) {   // all of this warp's TMEM reads are done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
         }
-        if (valid) {
-{
-            const int co = nt * p.BN + c0;
-            const int cnt = min(16, p.Cout - co);
-            if (cnt > 0) {
-              float y[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) y[i] = act_apply(v[i] + __ldg(p.bias + co + i), p.act);
-              store_split16(p.out_hi + obase + co, p.out_lo + obase + co, y, cnt);
-            }
-          }
-        }
+        if (valid) epilogue_store<2>(v, bias_s, nt * p.BN + c0, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
+      }
+      if (c0 < p.BN) {   // BN is a multiple of 16: one trailing 16-column group
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
+        if (valid) epilogue_store<1>(v, bias_s, nt * p.BN + c0, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
       }
       if (++acc == 2) {
         acc = 0;
@@ -412,9 +413,9 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048);
   }
-  const int dyn = max_smem - 1024;   // static barriers live in the remaining 1 KiB
+  const int dyn = max_smem - 2048;   // static barriers + staged bias live in the remaining 2 KiB
   p.stages = (dyn - 1024) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) {

@@ -29,13 +29,12 @@ namespace vr {
 static constexpr int kRowsThreads = 192;
 static constexpr int kR = 8;                       // output rows per CTA tile
 static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
-static constexpr int kAPlane = 17 * 1024;          // 130 * 128 B = 16640, padded to a 1 KiB multiple
-static constexpr int kASlot = 2 * kAPlane;         // hi + lo
-static constexpr int kASlots = 2;
+static constexpr int kMaxASlots = 8;
 
 struct RowsParams {
   int N, H, W, tiles_w, tiles_h, n_tiles, total_tiles;
   int chunks, CinPadR, BN, Cout, act;
+  int KB, ksteps, a_plane, a_slot, n_aslots, sbo, layout;   // channel-chunk width 64 (SW128) or 32 (SW64)
   int b_kw_bytes, b_buf_bytes;
   uint32_t idesc0;   // instruction descriptor without the N field
   bf16* out_hi;
@@ -51,24 +50,25 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_afull[kASlots];
-  __shared__ __align__(8) uint64_t bar_aempty[kASlots];
+  __shared__ __align__(8) uint64_t bar_afull[kMaxASlots];
+  __shared__ __align__(8) uint64_t bar_aempty[kMaxASlots];
   __shared__ __align__(8) uint64_t bar_bfull[2];
   __shared__ __align__(8) uint64_t bar_bempty[2];
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[256];   // folded-BN bias of every N tile, staged once (a global load per use stalled the epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + (uint32_t)(kASlots * kASlot);
+  const uint32_t b_base = smem_base + (uint32_t)(p.n_aslots * p.a_slot);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < kASlots; ++s) {
+    for (int s = 0; s < p.n_aslots; ++s) {
       mbar_init(smem_u32(&bar_afull[s]), 1);
       mbar_init(smem_u32(&bar_aempty[s]), 1);
     }
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             mbar_expect_tx(bfull, (uint32_t)(3 * p.b_kw_bytes));
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
-              tma_load_3d(bdst + (uint32_t)(kw * p.b_kw_bytes), &tmB, kw * p.CinPadR + cc * 64, nt * 3 * p.BN, 0,
+              tma_load_3d(bdst + (uint32_t)(kw * p.b_kw_bytes), &tmB, kw * p.CinPadR + cc * p.KB, nt * 3 * p.BN, 0,
                           bfull);
           }
           __syncwarp();
@@ -122,14 +123,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
           for (int r = 0; r < kR + 2; ++r) {
             mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
             const uint32_t afull = smem_u32(&bar_afull[as]);
-            const uint32_t adst = a_base + (uint32_t)(as * kASlot);
+            const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
             if (elect_one_sync()) {
-              mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * 128));
-              tma_load_5d(adst, &tmA, cc * 64, w0 - 1, h0 - 1 + r, n, 0, afull);
-              tma_load_5d(adst + (uint32_t)kAPlane, &tmA, cc * 64, w0 - 1, h0 - 1 + r, n, 1, afull);
+              mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * p.KB * 2));
+              tma_load_5d(adst, &tmA, cc * p.KB, w0 - 1, h0 - 1 + r, n, 0, afull);
+              tma_load_5d(adst + (uint32_t)p.a_plane, &tmA, cc * p.KB, w0 - 1, h0 - 1 + r, n, 1, afull);
             }
             __syncwarp();
-            if (++as == kASlots) {
+            if (++as == p.n_aslots) {
               as = 0;
               aph ^= 1u;
             }
@@ -142,8 +143,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     {
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, acc_phase = 0;
-      const uint32_t b3_plane = (uint32_t)(3 * p.BN * 128);   // hi -> lo plane inside one kw slab
-      const uint32_t dhi = desc_hi(1024, 2);
+      const uint32_t row_bytes = (uint32_t)(p.KB * 2);
+      const uint32_t b3_plane = (uint32_t)(3 * p.BN) * row_bytes;   // hi -> lo plane inside one kw slab
+      const uint32_t dhi = desc_hi((uint32_t)p.sbo, (uint32_t)p.layout);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
@@ -154,15 +156,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
           for (int r = 0; r < kR + 2; ++r) {
             mbar_wait(smem_u32(&bar_afull[as]), aph);
             tc_fence_after();
-            const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * kASlot));
-            const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * kASlot + kAPlane));
+            const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * p.a_slot));
+            const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * p.a_slot + p.a_plane));
             // input row r feeds output rows o = r-kh; accumulators o_lo..o_hi are adjacent TMEM column blocks
             const int o_lo = r - 2 < 0 ? 0 : r - 2;
             const int o_hi = r > kR - 1 ? kR - 1 : r;
             const int cnt = o_hi - o_lo + 1;
             const uint32_t d_tmem = d_set + (uint32_t)(o_lo * p.BN);
             // weight rows are stacked [kh=2 | kh=1 | kh=0]; block of accumulator o_lo is kh = r - o_lo
-            const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN * 128);
+            const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN) * row_bytes;
             const uint32_t idesc_all = p.idesc0 | ((uint32_t)((cnt * p.BN) >> 3) << 17);
             const bool fresh = cc == 0 && r <= kR - 1;   // accumulator r receives its first product now
 #pragma unroll
@@ -171,14 +173,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
               const uint32_t bk_lo = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b3_plane + b_row0);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t ao = (uint32_t)((kw * 128 + ks * 32) >> 4);
+                if (ks >= p.ksteps) break;
+                const uint32_t ao = ((uint32_t)kw * row_bytes + (uint32_t)(ks * 32)) >> 4;
                 const uint32_t ko = (uint32_t)((ks * 32) >> 4);
                 if (kw == 0 && ks == 0 && fresh) {
                   // first touch of accumulator r must overwrite: split the stacked MMA once
                   const uint32_t n_old = (uint32_t)((cnt - 1) * p.BN);
                   const uint32_t idesc_old = p.idesc0 | ((n_old >> 3) << 17);
                   const uint32_t idesc_new = p.idesc0 | ((uint32_t)(p.BN >> 3) << 17);
-                  const uint32_t bn_off = (uint32_t)(((cnt - 1) * p.BN * 128) >> 4);
+                  const uint32_t bn_off = ((uint32_t)((cnt - 1) * p.BN) * row_bytes) >> 4;
                   if (elect_one_sync()) {
                     if (cnt > 1) {
                       umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_old, 1u);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             }
             __syncwarp();
             if (elect_one_sync()) umma_commit(smem_u32(&bar_aempty[as]));
-            if (++as == kASlots) {
+            if (++as == p.n_aslots) {
               as = 0;
               aph ^= 1u;
             }
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int px = q * 32 + lane;
+    const float slope = p.act == ACT_RELU ? 0.f : p.act == ACT_LEAKY ? 0.01f : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -236,24 +240,25 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       const uint32_t t_set = tmem_base + (uint32_t)(acc * kR * p.BN) + ((uint32_t)(q * 32) << 16);
       for (int orow = 0; orow < kR; ++orow) {
         const int64_t obase = (int64_t)n * p.osn + (int64_t)(h0 + orow) * p.osh + (int64_t)(w0 + px) * p.osw;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(t_set + (uint32_t)(orow * p.BN + c0), v);
-          if (orow == kR - 1 && c0 + 16 >= p.BN) {
+        const bool last_row = orow == kR - 1;
+        if (p.BN == 32) {
+          float v[32];
+          tmem_ld32(t_set + (uint32_t)(orow * 32), v);
+          if (last_row) {   // all of this warp's TMEM reads are done: hand the accumulator set back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
           }
-{
-            const int co = nt * p.BN + c0;
-            const int cnt = min(16, p.Cout - co);
-            if (cnt > 0) {
-              float y[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) y[i] = act_apply(v[i] + __ldg(p.bias + co + i), p.act);
-              store_split16(p.out_hi + obase + co, p.out_lo + obase + co, y, cnt);
-            }
+          epilogue_store<2>(v, bias_s, nt * 32, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
+        } else {
+          float v[16];
+          tmem_ld16(t_set + (uint32_t)(orow * 16), v);
+          if (last_row) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
           }
+          epilogue_store<1>(v, bias_s, nt * 16, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
         }
       }
       if (++acc == 2) {
@@ -280,8 +285,9 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
   const int cout16 = round_up(L.Cout, 16);
   R.BN = cout16 == 16 ? 16 : 32;
   R.n_tiles = ceil_div(cout16, R.BN);
-  R.CinPadR = round_up(L.CinPad, 64);
-  R.chunks = R.CinPadR / 64;
+  R.KB = g_tc_debug[2] == 64 ? 64 : 32;   // channel-chunk width: 32 (SW64, deep row pipeline) unless forced to 64
+  R.CinPadR = round_up(L.CinPad, R.KB);
+  R.chunks = R.CinPadR / R.KB;
   // B[plane][nt*3*BN + (2-kh)*BN + co][kw*CinPadR + ci]: the three kh taps stacked along the MMA N dimension
   const int rows = R.n_tiles * R.BN;
   const int brows = 3 * rows;
@@ -317,10 +323,11 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
   R.bias = (float*)db;
   cuuint64_t dims[3] = {(cuuint64_t)Ktot, (cuuint64_t)brows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)Ktot * 2, (cuuint64_t)brows * Ktot * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)(3 * R.BN), 2};
+  cuuint32_t box[3] = {(cuuint32_t)R.KB, (cuuint32_t)(3 * R.BN), 2};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = tc_encode_fn()(&R.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dw, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              R.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     err = "cuTensorMapEncodeTiled(row-kernel weights) failed for " + L.name + " code " + std::to_string((int)r);
@@ -353,10 +360,11 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
       return cudaErrorInvalidValue;
     }
     cuuint64_t strides[4] = {(cuuint64_t)in.sw * 2, (cuuint64_t)in.sh * 2, (cuuint64_t)in.sn * 2, (cuuint64_t)plane};
-    cuuint32_t box[5] = {64, (cuuint32_t)kRowPx, 1, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)R.KB, (cuuint32_t)kRowPx, 1, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = tc_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in.hi, dims, strides, box, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                R.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       err = "cuTensorMapEncodeTiled(row-kernel activations) failed for " + L.name + " code " + std::to_string((int)r);
@@ -369,7 +377,12 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.tiles_w = out.W / 128; p.tiles_h = out.H / kR; p.n_tiles = R.n_tiles;
   p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
   p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.BN = R.BN; p.Cout = L.Cout; p.act = L.act;
-  p.b_kw_bytes = 2 * 3 * R.BN * 128;
+  p.KB = R.KB; p.ksteps = R.KB / 16;
+  p.a_plane = round_up(kRowPx * R.KB * 2, 1024);
+  p.a_slot = 2 * p.a_plane;
+  p.sbo = 8 * R.KB * 2;
+  p.layout = R.KB == 64 ? 2 : 4;
+  p.b_kw_bytes = 2 * 3 * R.BN * R.KB * 2;
   p.b_buf_bytes = 3 * p.b_kw_bytes;
   p.idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   p.out_hi = out.hi; p.out_lo = out.lo;
@@ -377,17 +390,23 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.bias = R.bias;
   p.tmem_cols = 2 * kR * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
   p.bo_mode = g_tc_debug[0];
-  const int dyn = kASlots * kASlot + 2 * p.b_buf_bytes + 1024;
   static bool attr_set = false;
-  static int num_sms = 0;
+  static int num_sms = 0, max_smem = 0;
   if (!attr_set) {
-    int dev = 0, max_smem = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048);
     attr_set = true;
   }
+  p.n_aslots = (max_smem - 2048 - 1024 - 2 * p.b_buf_bytes) / p.a_slot;
+  if (p.n_aslots > kMaxASlots) p.n_aslots = kMaxASlots;
+  if (p.n_aslots < 2) {
+    err = "tc_rows_launch: shared memory too small";
+    return cudaErrorInvalidValue;
+  }
+  const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + 1024;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, p);
   return cudaGetLastError();

@@ -125,6 +125,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 
+// 32 accumulator columns of this thread's TMEM lane (row of the tile) in one instruction
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// bias + activation + split-bf16 store of `n16` groups of 16 channels of one pixel.
+// slope: 0 = ReLU, 0.01 = LeakyReLU, 1 = identity  (y = max(v,0) + slope*min(v,0), branch-free)
+template <int N16>
+__device__ __forceinline__ void epilogue_store(const float* v, const float* bias_s, int co, int Cout, float slope,
+                                               bf16* out_hi, bf16* out_lo) {
+#pragma unroll
+  for (int g = 0; g < N16; ++g) {
+    const int c = co + 16 * g;
+    const int cnt = min(16, Cout - c);
+    if (cnt > 0) {
+      float y[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float t = v[16 * g + i] + bias_s[c + i];
+        y[i] = fmaxf(t, 0.f) + slope * fminf(t, 0.f);
+      }
+      store_split16(out_hi + c, out_lo + c, y, cnt);
+    }
+  }
+}
+
 // same, with the matrix-base-offset field [49,52) for tiles that do not start on the swizzle repeat
 __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type,
                                                       uint32_t base_offset) {

@@ -13,7 +13,7 @@ typedef std::tuple<const void*, const void*, int, int, int, int> ViewKey;
 
 struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 128 == 0 (conv_tc_rows.cu)
   bool ok = false;
-  int CinPadR = 0, chunks = 0, BN = 0, n_tiles = 0;
+  int KB = 32, CinPadR = 0, chunks = 0, BN = 0, n_tiles = 0;
   bf16* w_planes = nullptr;   // [2][n_tiles*BN][9*CinPadR]
   float* bias = nullptr;      // [n_tiles*BN]
   CUtensorMap map_b;
@@ -41,6 +41,6 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err);
-extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable the rows kernel
+extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable it, [2] = 64: 64-channel chunks
 
 }  // namespace vr

@@ -66,6 +66,11 @@ def load_library():
         fn = getattr(lib, name)   # AttributeError if the ABI is out of sync
         fn.restype = res
         fn.argtypes = args
+    # validation knobs of the tensor-core kernels (see vr_debug_set in include/vr_b200.h)
+    if os.environ.get('VR_ROWS_KB'):
+        lib.vr_debug_set(2, int(os.environ['VR_ROWS_KB']))
+    if os.environ.get('VR_NO_ROWS'):
+        lib.vr_debug_set(1, int(os.environ['VR_NO_ROWS']))
     _lib = lib
     return lib
 
