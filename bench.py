@@ -268,10 +268,14 @@ def run_gpu(args):
                                    '(lib/synth.py)' % (int(seconds), n_windows, args.batch),
                        'l2': 'no flush needed: per-step working set (spectrogram %.0f MB + activations > 1 GB) exceeds '
                              'the 126 MB L2' % (2 * 1025 * T * 8 / 1e6),
-                       'parallelism': 'window-sharded x%d, one mask gather' % world},
+                       'parallelism': ('window-sharded x%d: STFT / net / inverse STFT per rank span, 4-byte max all-reduce, 8 KB '
+                                       'halo mask frame, overlap-add kernel stores its span into rank 0 HBM over NVLink'
+                                       % world) if world > 1 else 'single GPU'},
             'clocks': sampler.summary(),
             'e2e': {'value': seconds / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(2 * L * 4),
-                    'd2h_bytes_per_step': int(2 * 2 * Lo * 4)},
+                    'd2h_bytes_per_step': int(2 * 2 * Lo * 4),
+                    'note': 'bytes are totals over all ranks; with N > 1 every rank moves only its own slice of the '
+                            'wave / stems over its own PCIe link (lib/distributed.py, sharded mode)'},
             'gpu_launches': int(launches),
             'roofline': roof,
             'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -97,6 +97,18 @@ VR_API int vr_apply_mask(vr_ctx* ctx, const void* spec, const float* mask, int64
 VR_API int vr_apply_mask_istft(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, float* wave_inst,
                         float* wave_voc, void* stream);
 
+/* Shard-sized pieces of the three calls above for the multi-GPU path (lib/distributed.py): the STFT of frames
+ * [t0, t1) only, max|spec| over those frames (ranks all-reduce it to the normaliser of inference.py:74), and the
+ * masked inverse STFT of output hops [k0, k1) = samples [hop*k0, hop*k1) of wave_inst / wave_voc [2][hop*(T-1)],
+ * which may be peer-mapped buffers on another GPU (the overlap-add kernel then stores over NVLink).
+ * spec / mask are the full-size [2][bins][T] arrays; only the columns the range touches are read / written.  */
+VR_API int vr_stft_range(vr_ctx* ctx, const float* wave, int64_t L, void* spec, int64_t T, int64_t t0, int64_t t1,
+                  void* stream);
+VR_API int vr_normaliser_range(vr_ctx* ctx, const void* spec, int64_t T, int64_t t0, int64_t t1, float* out,
+                        void* stream);
+VR_API int vr_apply_mask_istft_range(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, int64_t k0,
+                              int64_t k1, float* wave_inst, float* wave_voc, void* stream);
+
 /* Whole hot path with everything resident in HBM (inference.py:147-176 minus file I/O).                 */
 VR_API int vr_separate_wave(vr_ctx* ctx, const float* wave, int64_t L, int32_t tta, float* wave_inst,
                      float* wave_voc, void* stream);

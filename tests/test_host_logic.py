@@ -117,3 +117,23 @@ def test_sharded_gather_world_size_2_gloo(tmp_path):
     mask = torch.load(out)
     assert mask.shape == (2, 5, n_frames)
     assert torch.equal(mask[0, 0], torch.arange(n_frames, dtype=torch.float32))
+
+
+def test_shard_plan_tiles_the_track():
+    from lib import distributed
+    for T in (431, 1292, 10336, 20672, 82688, 103360):
+        for world in (2, 3, 4, 8):
+            n_windows, roi = distributed.window_count(T, 256, 64)
+            if n_windows < world:
+                continue
+            plans = [distributed.shard_plan(T, 256, 64, world, r) for r in range(world)]
+            hops = [(p[7], p[8]) for p in plans]
+            assert hops[0][0] == 0 and hops[-1][1] == T - 1
+            for (x0, x1), (y0, y1) in zip(hops, hops[1:]):
+                assert x1 == y0                                   # output spans tile [0, T-1)
+            for first, count, roi_, f0, f1, a, b, k0, k1 in plans:
+                assert a <= f0 <= f1 <= b or count == 0            # the rank's STFT span covers its mask frames
+                if count > 0 and f1 < T:
+                    assert f1 < b                                  # ... and the halo frame of its last output hop
+                if count > 0:
+                    assert a == max(0, first * roi_ - 64)           # exactly what its windows read (inference.py:44-50)

@@ -143,6 +143,25 @@ int vr_apply_mask_istft(vr_ctx* ctx, const void* spec, const float* mask, int64_
   return done(ctx, ctx->eng->istft((const float2*)spec, mask, T, wave_inst, wave_voc, (cudaStream_t)stream));
 }
 
+int vr_stft_range(vr_ctx* ctx, const float* wave, int64_t L, void* spec, int64_t T, int64_t t0, int64_t t1,
+                  void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->stft_range(wave, L, (float2*)spec, T, t0, t1, (cudaStream_t)stream));
+}
+
+int vr_normaliser_range(vr_ctx* ctx, const void* spec, int64_t T, int64_t t0, int64_t t1, float* out, void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->normaliser_range((const float2*)spec, T, t0, t1, out, (cudaStream_t)stream));
+}
+
+int vr_apply_mask_istft_range(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, int64_t k0, int64_t k1,
+                              float* wave_inst, float* wave_voc, void* stream) {
+  CHECK_CTX(ctx);
+  if (!mask) return fail(ctx, "vr_apply_mask_istft_range: mask is NULL");
+  return done(ctx, ctx->eng->istft_range((const float2*)spec, mask, T, k0, k1, wave_inst, wave_voc,
+                                         (cudaStream_t)stream));
+}
+
 int vr_separate_wave(vr_ctx* ctx, const float* wave, int64_t L, int32_t tta, float* wave_inst, float* wave_voc,
                      void* stream) {
   CHECK_CTX(ctx);

@@ -273,6 +273,31 @@ cudaError_t launch_absmax(const float2* spec, int64_t n, float* out_absmax, cuda
   return cudaGetLastError();
 }
 
+__global__ void absmax_range_kernel(const float2* __restrict__ spec, int nrows, int64_t T, int64_t t0, int64_t t1,
+                                    float* out) {
+  const int64_t span = t1 - t0;
+  const int64_t n = (int64_t)nrows * span;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / span;
+    const float2 v = spec[r * T + t0 + (i - r * span)];
+    m = fmaxf(m, hypotf(v.x, v.y));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));   // m >= 0
+}
+
+cudaError_t launch_absmax_range(const float2* spec, int nrows, int64_t T, int64_t t0, int64_t t1, float* out_absmax,
+                                cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out_absmax, 0, sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  const int64_t n = (int64_t)nrows * (t1 - t0);
+  if (n <= 0) return cudaSuccess;
+  int grid = (int)(((n + 255) / 256) < 148 * 8 ? ((n + 255) / 256) : 148 * 8);
+  absmax_range_kernel<<<grid, 256, 0, stream>>>(spec, nrows, T, t0, t1, out_absmax);
+  return cudaGetLastError();
+}
+
 // numpy's max() of a complex array is lexicographic (largest real part, ties by imaginary part);
 // separate_tta divides by that complex number (inference.py:87,94), so the net sees |X| / |lexmax|.
 __device__ __forceinline__ unsigned int order_key(float f) {

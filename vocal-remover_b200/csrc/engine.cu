@@ -630,15 +630,34 @@ bool Engine::apply_mask(const float2* spec, const float* mask, int64_t T, float2
 }
 
 bool Engine::stft(const float* wave, int64_t L, float2* spec, int64_t T, float* absmax, cudaStream_t s) {
+  if (!stft_range(wave, L, spec, T, 0, T, s)) return false;
+  if (absmax) return normaliser(spec, T, 0, absmax, s);
+  return true;
+}
+
+// frames [t0, t1) of the track only: what a rank of the window-sharded path needs (lib/distributed.py)
+bool Engine::stft_range(const float* wave, int64_t L, float2* spec, int64_t T, int64_t t0, int64_t t1, cudaStream_t s) {
   cudaSetDevice(cfg_.device);
   if (T != 1 + L / cfg_.hop) {
     err = "stft: T must equal 1 + L // hop_length";
     return false;
   }
+  if (t0 < 0 || t1 > T || t0 > t1) {
+    err = "stft: frame range outside [0, T]";
+    return false;
+  }
   ++launches;
-  if (!ck(launch_stft(wave, L, cfg_.n_fft, cfg_.hop, spec, T, twiddle_, window_, s), "stft")) return false;
-  if (absmax) return normaliser(spec, T, 0, absmax, s);
-  return true;
+  return ck(launch_stft(wave, L, cfg_.n_fft, cfg_.hop, spec, T, t0, t1, twiddle_, window_, s), "stft");
+}
+
+bool Engine::normaliser_range(const float2* spec, int64_t T, int64_t t0, int64_t t1, float* out, cudaStream_t s) {
+  cudaSetDevice(cfg_.device);
+  if (t0 < 0 || t1 > T || t0 > t1) {
+    err = "normaliser: frame range outside [0, T]";
+    return false;
+  }
+  ++launches;
+  return ck(launch_absmax_range(spec, 2 * bins(), T, t0, t1, out, s), "absmax range");
 }
 
 bool Engine::ensure_ws(int64_t T) {
@@ -666,19 +685,40 @@ bool Engine::ensure_ws(int64_t T) {
 }
 
 bool Engine::istft(const float2* spec, const float* mask, int64_t T, float* wave_a, float* wave_b, cudaStream_t s) {
+  return istft_range(spec, mask, T, 0, T - 1, wave_a, wave_b, s);
+}
+
+// Output hops [k0, k1) (samples [hop*k0, hop*k1)) of wave [2][hop*(T-1)]; reads frames of spec / mask that overlap
+// them (k0 - n_fft/hop/2 + 1 .. k1 + n_fft/hop/2 - 1 clipped to the track; k0..k1 for hop = n_fft/2).
+// wave_a / wave_b may point into another GPU's memory (peer-mapped).
+bool Engine::istft_range(const float2* spec, const float* mask, int64_t T, int64_t k0, int64_t k1, float* wave_a,
+                         float* wave_b, cudaStream_t s) {
   cudaSetDevice(cfg_.device);
-  const int64_t nfr = (int64_t)4 * T * cfg_.n_fft;
-  if (nfr > ws_frames_cap_) {
+  if (k0 < 0 || k1 > T - 1 || k0 > k1) {
+    err = "istft: hop range outside [0, T-1]";
+    return false;
+  }
+  if (k1 == k0) return true;
+  const int NF = cfg_.n_fft, hop = cfg_.hop;
+  // first / last frame touching samples [hop*k0, hop*k1): u = s + NF/2, frames ceil((u-NF+1)/hop) .. floor(u/hop)
+  int64_t f0 = ((int64_t)hop * k0 + NF / 2 - NF + hop) / hop;
+  if ((int64_t)hop * k0 + NF / 2 - NF + 1 <= 0) f0 = 0;
+  int64_t f1 = ((int64_t)hop * k1 - 1 + NF / 2) / hop;
+  if (f1 > T - 1) f1 = T - 1;
+  const int64_t nfr = f1 - f0 + 1;
+  const int64_t need = (int64_t)4 * nfr * NF;
+  if (need > ws_frames_cap_) {
     if (ws_frames_) cudaFree(ws_frames_);
     ws_frames_ = nullptr;
-    if (!ck(cudaMalloc(&ws_frames_, sizeof(float) * nfr), "workspace frames")) return false;
-    ws_frames_cap_ = nfr;
+    if (!ck(cudaMalloc(&ws_frames_, sizeof(float) * need), "workspace frames")) return false;
+    ws_frames_cap_ = need;
   }
   float* fa = ws_frames_;
-  float* fb = mask ? ws_frames_ + (int64_t)2 * T * cfg_.n_fft : nullptr;
+  float* fb = mask ? ws_frames_ + (int64_t)2 * nfr * NF : nullptr;
   launches += 2;
-  if (!ck(launch_istft_frames(spec, mask, cfg_.n_fft, T, fa, fb, twiddle_, window_, s), "istft frames")) return false;
-  return ck(launch_istft_ola(fa, fb, cfg_.n_fft, cfg_.hop, T, wave_a, mask ? wave_b : nullptr, window_, s),
+  if (!ck(launch_istft_frames(spec, mask, NF, T, f0, nfr, fa, fb, twiddle_, window_, s), "istft frames")) return false;
+  return ck(launch_istft_ola(fa, fb, NF, hop, T, f0, nfr, (int64_t)hop * k0, (int64_t)hop * k1, wave_a,
+                             mask ? wave_b : nullptr, window_, s),
             "istft ola");
 }
 

@@ -95,6 +95,10 @@ class Engine {
   // ---- reference-surface operations (device pointers) ----
   bool stft(const float* wave, int64_t L, float2* spec, int64_t T, float* absmax, cudaStream_t s);
   bool istft(const float2* spec, const float* mask, int64_t T, float* wave_a, float* wave_b, cudaStream_t s);
+  bool stft_range(const float* wave, int64_t L, float2* spec, int64_t T, int64_t t0, int64_t t1, cudaStream_t s);
+  bool normaliser_range(const float2* spec, int64_t T, int64_t t0, int64_t t1, float* out, cudaStream_t s);
+  bool istft_range(const float2* spec, const float* mask, int64_t T, int64_t k0, int64_t k1, float* wave_a,
+                   float* wave_b, cudaStream_t s);
   bool predict_mask(const float* mag, int N, float* mask_out, int offset, cudaStream_t s);
   // windows [first, first+count) of the padded spectrogram -> mask frames; see include/vr_b200.h
   bool separate_windows(const float2* spec, int64_t T, const float* norm, int pad_l, int first, int count,

@@ -41,10 +41,10 @@ __device__ __forceinline__ void fft_inplace(float2* z, const float2* __restrict_
 }
 
 __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wave, int64_t L, int NF, int logn,
-                                                   int hop, float2* __restrict__ spec, int64_t T,
+                                                   int hop, float2* __restrict__ spec, int64_t T, int64_t t_first,
                                                    const float2* __restrict__ tw, const float* __restrict__ win) {
   extern __shared__ float2 z[];
-  const int64_t t = blockIdx.x;
+  const int64_t t = t_first + blockIdx.x;
   const int64_t s0 = t * hop - NF / 2;
   for (int n = threadIdx.x; n < NF; n += blockDim.x) {
     const int64_t s = s0 + n;
@@ -67,26 +67,27 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ wav
   }
 }
 
-cudaError_t launch_stft(const float* wave, int64_t L, int n_fft, int hop, float2* spec, int64_t T,
-                        const float2* twiddle, const float* window, cudaStream_t stream) {
-  if (T == 0) return cudaSuccess;
+cudaError_t launch_stft(const float* wave, int64_t L, int n_fft, int hop, float2* spec, int64_t T, int64_t t0,
+                        int64_t t1, const float2* twiddle, const float* window, cudaStream_t stream) {
+  if (t1 <= t0) return cudaSuccess;
   int logn = 0;
   while ((1 << logn) < n_fft) ++logn;
   if ((1 << logn) != n_fft || n_fft > 4096 || n_fft < 64) return cudaErrorInvalidValue;
-  stft_kernel<<<(unsigned)T, 256, n_fft * sizeof(float2), stream>>>(wave, L, n_fft, logn, hop, spec, T, twiddle,
-                                                                    window);
+  stft_kernel<<<(unsigned)(t1 - t0), 256, n_fft * sizeof(float2), stream>>>(wave, L, n_fft, logn, hop, spec, T, t0,
+                                                                             twiddle, window);
   return cudaGetLastError();
 }
 
 // grid (T, 2 channels): windowed inverse transform of one frame of one channel -> frames[stem][c][t][NF]
 __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restrict__ spec,
                                                            const float* __restrict__ mask, int NF, int logn,
-                                                           int64_t T, float* __restrict__ frames_a,
+                                                           int64_t T, int64_t t_first, int64_t nfr,
+                                                           float* __restrict__ frames_a,
                                                            float* __restrict__ frames_b,
                                                            const float2* __restrict__ tw,
                                                            const float* __restrict__ win) {
   extern __shared__ float2 z[];
-  const int64_t t = blockIdx.x;
+  const int64_t t = t_first + blockIdx.x;
   const int c = blockIdx.y;
   const int bins = NF / 2 + 1;
   for (int k = threadIdx.x; k < bins; k += blockDim.x) {
@@ -116,8 +117,8 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restr
   __syncthreads();
   fft_inplace<true>(z, tw, NF, logn);
   const float inv = 1.f / (float)NF;
-  float* fa = frames_a + ((int64_t)c * T + t) * NF;
-  float* fb = frames_b ? frames_b + ((int64_t)c * T + t) * NF : nullptr;
+  float* fa = frames_a + ((int64_t)c * nfr + blockIdx.x) * NF;
+  float* fb = frames_b ? frames_b + ((int64_t)c * nfr + blockIdx.x) * NF : nullptr;
   for (int n = threadIdx.x; n < NF; n += blockDim.x) {
     const float w = win[n] * inv;
     fa[n] = z[n].x * w;
@@ -125,13 +126,16 @@ __global__ void __launch_bounds__(256) istft_frames_kernel(const float2* __restr
   }
 }
 
+// Output samples [s0, s1) of each channel; the scratch holds frames [t_first, t_first + nfr) of the track.
 __global__ void istft_ola_kernel(const float* __restrict__ frames_a, const float* __restrict__ frames_b, int NF,
-                                 int hop, int64_t T, int64_t Lo, float* __restrict__ wave_a,
-                                 float* __restrict__ wave_b, const float* __restrict__ win) {
+                                 int hop, int64_t T, int64_t t_first, int64_t nfr, int64_t s0, int64_t s1, int64_t Lo,
+                                 float* __restrict__ wave_a, float* __restrict__ wave_b,
+                                 const float* __restrict__ win) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * Lo) return;
-  const int c = (int)(idx / Lo);
-  const int64_t s = idx % Lo;
+  const int64_t span = s1 - s0;
+  if (idx >= 2 * span) return;
+  const int c = (int)(idx / span);
+  const int64_t s = s0 + idx % span;
   const int64_t u = s + NF / 2;
   int64_t t1 = u / hop;
   if (t1 > T - 1) t1 = T - 1;
@@ -142,36 +146,39 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames_a, const float
     const int n = (int)(u - t * hop);
     const float w = win[n];
     wss += w * w;
-    acc_a += frames_a[((int64_t)c * T + t) * NF + n];
-    if (frames_b) acc_b += frames_b[((int64_t)c * T + t) * NF + n];
+    const int64_t fi = ((int64_t)c * nfr + (t - t_first)) * NF + n;
+    acc_a += frames_a[fi];
+    if (frames_b) acc_b += frames_b[fi];
   }
   if (wss > 1.17549435e-38f) {   // np.finfo(float32).tiny
     acc_a /= wss;
     acc_b /= wss;
   }
-  wave_a[idx] = acc_a;
-  if (wave_b) wave_b[idx] = acc_b;
+  wave_a[(int64_t)c * Lo + s] = acc_a;
+  if (wave_b) wave_b[(int64_t)c * Lo + s] = acc_b;
 }
 
 // frames scratch is provided by the caller through wave-independent workspace (see engine.cu)
-cudaError_t launch_istft_frames(const float2* spec, const float* mask, int n_fft, int64_t T, float* frames_a,
-                                float* frames_b, const float2* twiddle, const float* window, cudaStream_t stream) {
-  if (T == 0) return cudaSuccess;
+cudaError_t launch_istft_frames(const float2* spec, const float* mask, int n_fft, int64_t T, int64_t t_first,
+                                int64_t nfr, float* frames_a, float* frames_b, const float2* twiddle,
+                                const float* window, cudaStream_t stream) {
+  if (nfr <= 0) return cudaSuccess;
   int logn = 0;
   while ((1 << logn) < n_fft) ++logn;
   if ((1 << logn) != n_fft || n_fft > 4096 || n_fft < 64) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)T, 2);
-  istft_frames_kernel<<<grid, 256, n_fft * sizeof(float2), stream>>>(spec, mask, n_fft, logn, T, frames_a, frames_b,
-                                                                     twiddle, window);
+  dim3 grid((unsigned)nfr, 2);
+  istft_frames_kernel<<<grid, 256, n_fft * sizeof(float2), stream>>>(spec, mask, n_fft, logn, T, t_first, nfr, frames_a,
+                                                                     frames_b, twiddle, window);
   return cudaGetLastError();
 }
 
 cudaError_t launch_istft_ola(const float* frames_a, const float* frames_b, int n_fft, int hop, int64_t T,
-                             float* wave_a, float* wave_b, const float* window, cudaStream_t stream) {
+                             int64_t t_first, int64_t nfr, int64_t s0, int64_t s1, float* wave_a, float* wave_b,
+                             const float* window, cudaStream_t stream) {
   const int64_t Lo = (int64_t)hop * (T - 1);
-  if (Lo <= 0) return cudaSuccess;
-  istft_ola_kernel<<<(unsigned)((2 * Lo + 255) / 256), 256, 0, stream>>>(frames_a, frames_b, n_fft, hop, T, Lo,
-                                                                         wave_a, wave_b, window);
+  if (s1 <= s0) return cudaSuccess;
+  istft_ola_kernel<<<(unsigned)((2 * (s1 - s0) + 255) / 256), 256, 0, stream>>>(frames_a, frames_b, n_fft, hop, T, t_first,
+                                                                                nfr, s0, s1, Lo, wave_a, wave_b, window);
   return cudaGetLastError();
 }
 

@@ -36,6 +36,9 @@ struct MaskOutParams {
 cudaError_t launch_mask_out(const MaskOutParams& p, cudaStream_t stream);
 
 cudaError_t launch_absmax(const float2* spec, int64_t n, float* out_absmax, cudaStream_t stream);
+// max |spec[r][t]| over rows r < nrows and frames t in [t0, t1) of a [nrows][T] array
+cudaError_t launch_absmax_range(const float2* spec, int nrows, int64_t T, int64_t t0, int64_t t1, float* out_absmax,
+                                cudaStream_t stream);
 cudaError_t launch_lexmax_abs(const float2* spec, int64_t n, unsigned long long* scratch, float* out_norm,
                               cudaStream_t stream);
 cudaError_t launch_apply_mask(const float2* spec, const float* mask, int64_t n, float2* y, float2* v,
@@ -56,14 +59,18 @@ cudaError_t launch_lstm_dense(const float* hs, const float* wd, const float* sca
                               int K, int bins, ActView dst, int ch, cudaStream_t stream);
 
 // ---- STFT / iSTFT (fft.cu), reference lib/spec_utils.py:26-31,157-165 (librosa semantics)
-cudaError_t launch_stft(const float* wave, int64_t L, int n_fft, int hop, float2* spec, int64_t T,
-                        const float2* twiddle, const float* window, cudaStream_t stream);
+// frames [t0, t1) only (the full-track call is t0 = 0, t1 = T)
+cudaError_t launch_stft(const float* wave, int64_t L, int n_fft, int hop, float2* spec, int64_t T, int64_t t0,
+                        int64_t t1, const float2* twiddle, const float* window, cudaStream_t stream);
 // frames_a[c][t][:] = hann * irfft(spec * mask), frames_b = hann * irfft(spec * (1 - mask));
 // mask == nullptr: frames_a = hann * irfft(spec), frames_b unused
-cudaError_t launch_istft_frames(const float2* spec, const float* mask, int n_fft, int64_t T, float* frames_a,
-                                float* frames_b, const float2* twiddle, const float* window, cudaStream_t stream);
-// overlap-add + window-sum-square normalisation + centre trim -> wave [2][hop*(T-1)]
+// frames [t_first, t_first + nfr) of the track into a scratch laid out [c][nfr][n_fft]
+cudaError_t launch_istft_frames(const float2* spec, const float* mask, int n_fft, int64_t T, int64_t t_first,
+                                int64_t nfr, float* frames_a, float* frames_b, const float2* twiddle,
+                                const float* window, cudaStream_t stream);
+// overlap-add + window-sum-square normalisation + centre trim of output samples [s0, s1) of wave [2][hop*(T-1)]
 cudaError_t launch_istft_ola(const float* frames_a, const float* frames_b, int n_fft, int hop, int64_t T,
-                             float* wave_a, float* wave_b, const float* window, cudaStream_t stream);
+                             int64_t t_first, int64_t nfr, int64_t s0, int64_t s1, float* wave_a, float* wave_b,
+                             const float* window, cudaStream_t stream);
 
 }  // namespace vr

@@ -1,19 +1,24 @@
 """Window-sharded multi-GPU execution of the hot path (one process per GPU).
 
-Windows of a track are independent given the global normaliser (inference.py:74; BN is eval-mode, the
-LSTM state is per window), so rank r runs a contiguous block of window indices and the masks meet on
-rank 0 before the overlap-add.  Every rank holds the wave, computes the (cheap) STFT and
-the normaliser itself, so the only exchange is the masks:
+Windows of a track are independent given the global normaliser (inference.py:74; BN is eval-mode, the LSTM
+state is per window), so rank r owns a contiguous block of window indices and, with it, the
+corresponding frame span of everything else on the path:
 
-* default (``VR_GATHER=p2p``): rank 0's whole-track mask buffer is mapped into every rank through CUDA IPC
-  and the mask epilogue kernel (sigmoid + crop of the last 1x1 conv) stores its shard straight into rank 0's
-  HBM over NVLink - compute and "gather" are one kernel; two tiny NCCL barriers order producers / consumer.
-* ``VR_GATHER=nccl``: one ``torch.distributed.gather`` of dense per-rank blocks (the plain-library baseline).
+* default (``VR_GATHER=sharded``, needs hop == n_fft/2 and no TTA): every stage is sharded.  A rank computes the
+  STFT of just the frames its windows read, max|X| over them (one 4-byte all-reduce gives the global normaliser),
+  its masks, receives ONE halo mask frame (8 KB) from its right neighbour, and runs the masked inverse STFT +
+  overlap-add of its own output span.  In the device-resident form the overlap-add kernel stores that span
+  straight into rank 0's stem buffers, which are mapped into every rank through CUDA IPC (compute + gather in one
+  kernel over NVLink); in the host form every rank moves only its own slice over PCIe.
+* ``VR_GATHER=p2p``: only the net is sharded; the mask epilogue kernel stores into rank 0's mask buffer over
+  NVLink, rank 0 runs the inverse STFT of the whole track.
+* ``VR_GATHER=nccl``: as p2p but with one ``torch.distributed.gather`` of dense mask blocks (library baseline).
 
 ``world == 1`` degenerates to the fused single-GPU call.
 """
 import ctypes
 import os
+
 import numpy as np
 import torch
 
@@ -55,13 +60,21 @@ def gather_blocks(block, world, rank, group=None):
     return gathered
 
 
-_shared = {}   # (ctx id, bytes) -> (device pointer, owner flag)
+_shared = {}   # (ctx id, tag, bytes) -> (device pointer, owner flag)
 
 
-def _shared_mask(ctx, nbytes, world, rank, dev, group):
-    """Rank 0's mask buffer, mapped on every rank (cached per context and size)."""
+class _RawCudaArray(object):
+    """Zero-copy torch view of a raw device pointer (``torch.as_tensor`` reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': '<f4', 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}
+
+
+def _shared_buffer(ctx, tag, nbytes, world, rank, dev, group):
+    """A buffer in rank 0's HBM, mapped on every rank (cached per context, tag and size)."""
     import torch.distributed as dist
-    key = (id(ctx), int(nbytes))
+    key = (id(ctx), tag, int(nbytes))
     if key in _shared:
         return _shared[key][0]
     handle = ctypes.create_string_buffer(64)
@@ -83,9 +96,95 @@ def separate_wave(sp, d_wave, tta=False, world=1, rank=0, group=None):
         raise NotImplementedError('multi-GPU --tta: shard files instead (SURVEY 8(f) rank 3)')
     if world == 1:
         return sp.separate_wave(d_wave, tta=tta)
-    if os.environ.get('VR_GATHER', 'p2p') == 'p2p':
+    mode = os.environ.get('VR_GATHER', 'sharded')
+    n_windows, _ = window_count(1 + d_wave.shape[1] // sp.model.hop_length, sp.cropsize, sp.offset)
+    if mode == 'sharded' and (sp.model.hop_length * 2 != sp.model.n_fft or n_windows < world):
+        mode = 'p2p'
+    if mode == 'sharded':
+        return _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0=True)
+    if mode == 'p2p':
         return _separate_wave_p2p(sp, d_wave, world, rank, group)
     return _separate_wave_nccl(sp, d_wave, world, rank, group)
+
+
+def shard_plan(n_frames, cropsize, offset, world, rank):
+    """Frame spans of one rank: (first, count, roi, f0, f1, a, b, k0, k1).
+
+    [f0, f1) mask frames it produces, [a, b) spectrogram frames its windows read (f1 < b whenever f1 < n_frames,
+    so the halo frame is included), [k0, k1) output hops it reconstructs (samples [hop*k0, hop*k1))."""
+    n_windows, roi = window_count(n_frames, cropsize, offset)
+    first, count, _ = shard_windows(n_windows, world, rank)
+    f0 = min(n_frames, first * roi)
+    f1 = min(n_frames, (first + count) * roi)
+    a = max(0, min(n_frames, first * roi - offset))
+    b = min(n_frames, (first + count) * roi + offset) if count > 0 else a
+    k0 = min(f0, n_frames - 1)
+    k1 = min(f1, n_frames - 1)
+    return first, count, roi, f0, f1, a, b, k0, k1
+
+
+def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=None):
+    """Everything sharded (see module docstring).  ``to_rank0``: stems are assembled in rank 0's HBM by the
+    overlap-add kernels (returns them on rank 0); otherwise each rank writes its span into ``local_out``."""
+    import torch.distributed as dist
+    ctx = sp._ctx()
+    dev = d_wave.device
+    hop, n_fft = sp.model.hop_length, sp.model.n_fft
+    bins = n_fft // 2 + 1
+    L = d_wave.shape[1]
+    T = 1 + L // hop
+    Lo = hop * (T - 1)
+    first, count, roi, f0, f1, a, b, k0, k1 = shard_plan(T, sp.cropsize, sp.offset, world, rank)
+    st = _native.stream_ptr()
+    with torch.cuda.device(dev):
+        key = ('ws', id(ctx), T)
+        if key not in _shared:
+            _shared[key] = (torch.empty((2, bins, T), dtype=torch.complex64, device=dev),
+                            torch.empty((2, bins, T), dtype=torch.float32, device=dev))
+        spec, mask = _shared[key]
+        norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        if b > a:
+            ctx.check(ctx.lib.vr_stft_range(ctx.handle, _native.ptr(d_wave), L, _native.ptr(spec), T, a, b, st),
+                      'vr_stft_range')
+            ctx.check(ctx.lib.vr_normaliser_range(ctx.handle, _native.ptr(spec), T, a, b, _native.ptr(norm), st),
+                      'vr_normaliser_range')
+        dist.all_reduce(norm, op=dist.ReduceOp.MAX, group=group)        # inference.py:74, 4 bytes
+        if count > 0:
+            ctx.check(ctx.lib.vr_separate_windows(ctx.handle, _native.ptr(spec), T, _native.ptr(norm), sp.offset,
+                                                  first, count, _native.ptr(mask), T, 0, 0, st),
+                      'vr_separate_windows')
+        # halo: output hop k needs frames k and k+1, so the last hop of this span needs the first mask frame of
+        # the right neighbour
+        ops = []
+        send_col = recv_col = None
+        if rank > 0 and count > 0 and f0 < T:
+            send_col = mask[:, :, f0].contiguous()
+            ops.append(dist.P2POp(dist.isend, send_col, rank - 1, group=group))
+        if count > 0 and f1 < T:
+            recv_col = torch.empty((2, bins), dtype=torch.float32, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv_col, rank + 1, group=group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if recv_col is not None:
+            mask[:, :, f1].copy_(recv_col)
+        if to_rank0:
+            inst_ptr = _shared_buffer(ctx, 'inst', 2 * Lo * 4, world, rank, dev, group)
+            voc_ptr = _shared_buffer(ctx, 'voc', 2 * Lo * 4, world, rank, dev, group)
+        else:
+            inst_ptr, voc_ptr = _native.ptr(local_out[0]), _native.ptr(local_out[1])
+        if k1 > k0:
+            ctx.check(ctx.lib.vr_apply_mask_istft_range(ctx.handle, _native.ptr(spec), _native.ptr(mask), T, k0, k1,
+                                                        inst_ptr, voc_ptr, st), 'vr_apply_mask_istft_range')
+        if not to_rank0:
+            return hop * k0, hop * k1
+        done = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.all_reduce(done, group=group)     # stream-ordered: every rank's remote stores precede it
+        if rank != 0:
+            return None, None
+        inst = torch.as_tensor(_RawCudaArray(inst_ptr.value, (2, Lo)), device=dev)
+        voc = torch.as_tensor(_RawCudaArray(voc_ptr.value, (2, Lo)), device=dev)
+        return inst, voc
 
 
 def _separate_wave_p2p(sp, d_wave, world, rank, group):
@@ -100,7 +199,7 @@ def _separate_wave_p2p(sp, d_wave, world, rank, group):
     first, count, per = shard_windows(n_windows, world, rank)
     st = _native.stream_ptr()
     with torch.cuda.device(dev):
-        mask_ptr = _shared_mask(ctx, 2 * bins * T * 4, world, rank, dev, group)
+        mask_ptr = _shared_buffer(ctx, 'mask', 2 * bins * T * 4, world, rank, dev, group)
         spec = torch.empty((2, bins, T), dtype=torch.complex64, device=dev)
         norm = torch.empty(1, dtype=torch.float32, device=dev)
         ctx.check(ctx.lib.vr_stft(ctx.handle, _native.ptr(d_wave), L, _native.ptr(spec), T, _native.ptr(norm), st),
@@ -109,8 +208,8 @@ def _separate_wave_p2p(sp, d_wave, world, rank, group):
             # the epilogue kernel writes frames [first*roi, (first+count)*roi) of rank 0's mask directly
             ctx.check(ctx.lib.vr_separate_windows(ctx.handle, _native.ptr(spec), T, _native.ptr(norm), sp.offset,
                                                   first, count, mask_ptr, T, 0, 0, st), 'vr_separate_windows')
-        torch.cuda.current_stream().synchronize()   # remote stores are complete when the kernels are
-        dist.barrier(group=group)                    # every shard has landed in rank 0's HBM
+        flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.all_reduce(flag, group=group)           # stream-ordered: every shard has landed in rank 0's HBM
         inst = voc = None
         if rank == 0:
             Lo = hop * (T - 1)
@@ -118,8 +217,7 @@ def _separate_wave_p2p(sp, d_wave, world, rank, group):
             voc = torch.empty((2, Lo), dtype=torch.float32, device=dev)
             ctx.check(ctx.lib.vr_apply_mask_istft(ctx.handle, _native.ptr(spec), mask_ptr, T, _native.ptr(inst),
                                                   _native.ptr(voc), st), 'vr_apply_mask_istft')
-            torch.cuda.current_stream().synchronize()
-        dist.barrier(group=group)                    # the mask may be overwritten by the next call from here on
+        dist.all_reduce(flag, group=group)           # the mask may be overwritten by the next call from here on
         return inst, voc
 
 
@@ -158,7 +256,12 @@ def _separate_wave_nccl(sp, d_wave, world, rank, group):
 
 
 def separate_wave_host(sp, h_wave, h_inst, h_voc, tta=False, world=1, rank=0, group=None):
-    """Host (pinned) wave -> host (pinned) stems on rank 0; H2D and D2H copies are part of the call."""
+    """Host (pinned) wave -> host (pinned) stems; H2D and D2H copies are part of the call.
+
+    world == 1: the whole track.  world > 1 (sharded mode): every rank copies in only the samples its frames read
+    and copies out only its own slice ``[:, s0:s1]`` of the stems into ITS ``h_inst`` / ``h_voc`` (returned as
+    (s0, s1)); the slices of all ranks tile the track.  Other modes leave the full stems on rank 0.
+    """
     dev = torch.device('cuda', sp._ctx().device_index)
     if world == 1:
         ctx = sp._ctx()
@@ -166,10 +269,38 @@ def separate_wave_host(sp, h_wave, h_inst, h_voc, tta=False, world=1, rank=0, gr
             ctx.check(ctx.lib.vr_separate_wave_host(ctx.handle, h_wave.data_ptr(), h_wave.shape[1], 1 if tta else 0,
                                                     h_inst.data_ptr(), h_voc.data_ptr(), _native.stream_ptr()),
                       'vr_separate_wave_host')
-        return
-    d_wave = h_wave.to(dev, non_blocking=True)
-    inst, voc = separate_wave(sp, d_wave, tta=tta, world=world, rank=rank, group=group)
-    if rank == 0:
-        h_inst.copy_(inst, non_blocking=True)
-        h_voc.copy_(voc, non_blocking=True)
-    torch.cuda.synchronize(dev)
+        return 0, h_inst.shape[1]
+    hop, n_fft = sp.model.hop_length, sp.model.n_fft
+    L = h_wave.shape[1]
+    T = 1 + L // hop
+    n_windows, _ = window_count(T, sp.cropsize, sp.offset)
+    mode = os.environ.get('VR_GATHER', 'sharded')
+    if mode != 'sharded' or tta or hop * 2 != n_fft or n_windows < world:
+        d_wave = h_wave.to(dev, non_blocking=True)
+        inst, voc = separate_wave(sp, d_wave, tta=tta, world=world, rank=rank, group=group)
+        if rank == 0:
+            h_inst.copy_(inst, non_blocking=True)
+            h_voc.copy_(voc, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return (0, h_inst.shape[1]) if rank == 0 else (0, 0)
+    _, _, _, _, _, a, b, _, _ = shard_plan(T, sp.cropsize, sp.offset, world, rank)
+    with torch.cuda.device(dev):
+        key = ('hostws', id(sp._ctx()), L)
+        if key not in _shared:
+            Lo = hop * (T - 1)
+            _shared[key] = (torch.empty((2, L), dtype=torch.float32, device=dev),
+                            torch.empty((2, Lo), dtype=torch.float32, device=dev),
+                            torch.empty((2, Lo), dtype=torch.float32, device=dev))
+        d_wave, d_inst, d_voc = _shared[key]
+        if b > a:   # samples read by frames [a, b)
+            w0 = max(0, a * hop - n_fft // 2)
+            w1 = min(L, (b - 1) * hop + n_fft // 2)
+            for c in range(2):   # row slices are contiguous: direct DMA from pinned memory, no host staging copy
+                d_wave[c, w0:w1].copy_(h_wave[c, w0:w1], non_blocking=True)
+        s0, s1 = _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0=False, local_out=(d_inst, d_voc))
+        if s1 > s0:
+            for c in range(2):
+                h_inst[c, s0:s1].copy_(d_inst[c, s0:s1], non_blocking=True)
+                h_voc[c, s0:s1].copy_(d_voc[c, s0:s1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return s0, s1
