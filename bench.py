@@ -243,7 +243,8 @@ def run_gpu(args):
     roof = None
     if tc_n > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel + conv_tc_rows_kernel (tcgen05 implicit-GEMM conv, bf16x3 split precision)',
+        roof = {'bound': 'tensor', 'kernel': 'conv_tc_rows_kernel + conv_tc_flat_kernel + conv_tc_kernel (tcgen05 implicit-GEMM conv family, '
+                          'bf16x3 split precision)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
                 'peak_source': peak_src,
                 'note': 'achieved = algorithmic conv FLOPs (real channel counts, 1x per product; the kernel issues 3 '

@@ -361,6 +361,7 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
     return false;
   }
   if (!tc_rows_prepare(L, *tc, err, allocs)) return false;
+  if (!tc_flat_prepare(L, *tc, err)) return false;
   L.tc = tc;
   return true;
 }
@@ -368,6 +369,7 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
 cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err) {
   TcConv& tc = *L.tc;
   if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err);
+  if (tc_flat_supported(L, tc, in, out)) return tc_flat_launch(L, tc, in, out, s, err);
   const TileGeom g = tile_geom(out.H, out.W);
   auto key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
   auto it = tc.map_a.find(key);

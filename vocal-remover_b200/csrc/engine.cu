@@ -31,10 +31,11 @@ void* Engine::dalloc(size_t bytes) {
   return p;
 }
 
-Buffer Engine::make_buffer(int N, int H, int W, int C) {
+Buffer Engine::make_buffer(int N, int H, int W, int C, int pad_w) {
   Buffer b;
   b.N = N; b.H = H; b.W = W; b.C = C;
-  size_t plane = (size_t)N * H * W * C * sizeof(bf16);
+  b.Wp = W + pad_w;
+  size_t plane = (size_t)N * H * b.Wp * C * sizeof(bf16);
   plane = (plane + 1023) / 1024 * 1024;
   char* p = (char*)dalloc(2 * plane);
   if (p) {
@@ -197,12 +198,16 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.cat1 = make_buffer(Nb, H, W, c1);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
-  P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
-  P.cat3 = make_buffer(Nb, H / 4, W / 4, 10 * n);
-  P.t4 = make_buffer(Nb, H / 8, W / 8, 6 * n);
-  P.cat4 = make_buffer(Nb, H / 8, W / 8, 14 * n);
-  P.t5 = make_buffer(Nb, H / 16, W / 16, 8 * n);
-  P.e5 = make_buffer(Nb, H / 16, W / 16, 8 * n);
+  // Feature maps that feed a 3x3 stride-1 convolution at W <= 64 carry zero pad pixels after every row (>= the
+  // horizontal dilation of their consumers: 1, or 6 for the ASPP input) so that the flat-halo kernel can read the
+  // taps as shifted views of one contiguous pixel segment.
+  const int pw = (W / 4 <= 64) ? 2 : 0;
+  P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n, pw);
+  P.cat3 = make_buffer(Nb, H / 4, W / 4, 10 * n, pw);
+  P.t4 = make_buffer(Nb, H / 8, W / 8, 6 * n, pw);
+  P.cat4 = make_buffer(Nb, H / 8, W / 8, 14 * n, pw);
+  P.t5 = make_buffer(Nb, H / 16, W / 16, 8 * n, pw);
+  P.e5 = make_buffer(Nb, H / 16, W / 16, 8 * n, pw ? 6 : 0);
   P.pool = make_buffer(Nb, 1, W / 16, 8 * n);
   P.f1 = make_buffer(Nb, 1, W / 16, 8 * n);
   P.acat = make_buffer(Nb, H / 16, W / 16, 40 * n);
@@ -382,10 +387,7 @@ bool Engine::finalize() {
   cudaMemcpy(out_w_, ow->data.data(), sizeof(float) * 2 * nout, cudaMemcpyHostToDevice);
   // strict load: no unexpected keys (torch load_state_dict(strict=True), inference.py:131)
   {
-    size_t expected = 2;
-    auto count_net = [&](int) { return (size_t)135; };
-    (void)count_net;
-    // every key we did not consume is unexpected; cheap check by prefix
+    // every key outside the model's name space is unexpected
     for (auto& kv : sd_) {
       const std::string& k = kv.first;
       bool ok = k == "out.weight" || k == "aux_out.weight" || k.rfind("stg1_low_band_net.", 0) == 0 ||
@@ -396,7 +398,6 @@ bool Engine::finalize() {
         return false;
       }
     }
-    (void)expected;
   }
   if (!ck(cudaDeviceSynchronize(), "finalize")) return false;
   finalized_ = true;
@@ -762,7 +763,7 @@ bool Engine::debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   std::vector<void*> tmp;
   std::swap(tmp, allocs_);
-  Buffer bin = make_buffer(N, H, W, cin_pad);
+  Buffer bin = make_buffer(N, H, W, cin_pad, W <= 64 ? (dil_w > 2 ? dil_w : 2) : 0);   // pad pixels: flat-halo kernel
   Buffer bout = make_buffer(N, Ho, Wo, round_up(Cout, 8));
   ConvLayer L;
   L.name = "debug_conv";

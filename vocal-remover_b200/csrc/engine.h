@@ -23,14 +23,16 @@ struct Buffer {   // a whole NHWC split-bf16 allocation
   bf16* hi = nullptr;
   bf16* lo = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
+  int Wp = 0;   // row pitch in pixels (>= W): the Wp - W trailing pixels of every row are permanent zeros, which
+                // is the horizontal conv padding of the flat-halo tensor-core kernel (conv_tc_flat.cu)
   ActView view(int n, int h0, int h, int c0, int c) const {
     ActView v;
-    const int64_t off = (int64_t)h0 * W * C + c0;
+    const int64_t off = (int64_t)h0 * Wp * C + c0;
     v.hi = hi + off;
     v.lo = lo + off;
     v.N = n; v.H = h; v.W = W; v.C = c;
-    v.sn = (int64_t)H * W * C;
-    v.sh = (int64_t)W * C;
+    v.sn = (int64_t)H * Wp * C;
+    v.sh = (int64_t)Wp * C;
     v.sw = C;
     return v;
   }
@@ -161,7 +163,7 @@ class Engine {
   float* out_w_ = nullptr;     // [2][nout]
 
   void* dalloc(size_t bytes);
-  Buffer make_buffer(int N, int H, int W, int C);
+  Buffer make_buffer(int N, int H, int W, int C, int pad_w = 0);
   bool need(const std::string& key, std::initializer_list<int64_t> shape, const HostTensor** out);
   bool make_conv(ConvLayer& L, const std::string& prefix, const std::vector<int>& perm, int cin_pad, int k, int stride,
                  int dh, int dw, int act);

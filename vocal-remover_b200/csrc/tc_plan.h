@@ -20,6 +20,12 @@ struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 1
   std::map<ViewKey, CUtensorMap> map_a;
 };
 
+struct TcFlatPlan {   // flat-halo variant: 3x3, stride 1, W <= 64 with zero pad pixels after every row (conv_tc_flat.cu)
+  bool ok = false;
+  CUtensorMap map_b;
+  std::map<ViewKey, CUtensorMap> map_a;
+};
+
 struct TcConv {
   int CinPadTC = 0, KB = 0, cchunks = 0, SUBS = 0, taps = 0, Ktot = 0, CoutPadN = 0, BN = 0, n_tiles = 0;
   bf16* w_planes = nullptr;   // [2][CoutPadN][Ktot]
@@ -27,6 +33,7 @@ struct TcConv {
   CUtensorMap map_b;
   std::map<ViewKey, CUtensorMap> map_a;
   TcRowsPlan rows;
+  TcFlatPlan flat;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -41,6 +48,11 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err);
-extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable it, [2] = 64: 64-channel chunks
+// conv_tc_flat.cu
+bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err);
+bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
+cudaError_t tc_flat_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
+                           std::string& err);
+extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable it, [2] = 64: 64-channel chunks, [3] disable the flat-halo kernel
 
 }  // namespace vr
