@@ -25,6 +25,11 @@ def _newest_header():
 
 
 def build(verbose=False, force=False):
+    global OBJ, LIB
+    extra = os.environ.get('VR_BUILD_FLAGS', '').split()
+    if os.environ.get('VR_BUILD_TAG'):
+        OBJ = os.path.join(HERE, 'build_' + os.environ['VR_BUILD_TAG'])
+        LIB = os.path.join(HERE, 'libvr_b200_%s.so' % os.environ['VR_BUILD_TAG'])
     os.makedirs(OBJ, exist_ok=True)
     hdr = _newest_header()
     jobs = []
@@ -36,7 +41,7 @@ def build(verbose=False, force=False):
 
     def cc(job):
         s, o = job
-        cmd = [NVCC] + FLAGS + ['-c', s, '-o', o]
+        cmd = [NVCC] + FLAGS + extra + ['-c', s, '-o', o]
         if verbose:
             cmd += ['-Xptxas', '-v']
         r = subprocess.run(cmd, capture_output=True, text=True)

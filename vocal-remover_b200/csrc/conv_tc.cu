@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       const int ksteps = p.KB / 16;
+      const uint32_t dhi = desc_hi(p.sbo_bytes, p.layout_type);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
@@ -148,20 +149,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int nsub = min(p.SUBS, p.total_sub - it * p.SUBS);
           const uint32_t sbase = smem_base + (uint32_t)(stage * stage_bytes);
           for (int j = 0; j < nsub; ++j) {
-            const uint32_t a_hi = sbase + (uint32_t)(j * p.a_sub_bytes);
-            const uint32_t a_lo = a_hi + (uint32_t)p.a_plane_bytes;
-            const uint32_t b_hi = sbase + (uint32_t)(b_region + j * p.b_sub_bytes);
-            const uint32_t b_lo = b_hi + (uint32_t)p.b_plane_bytes;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ko = (uint32_t)(k * 32);
-              const uint64_t da_hi = make_smem_desc(a_hi + ko, p.sbo_bytes, p.layout_type);
-              const uint64_t da_lo = make_smem_desc(a_lo + ko, p.sbo_bytes, p.layout_type);
-              const uint64_t db_hi = make_smem_desc(b_hi + ko, p.sbo_bytes, p.layout_type);
-              const uint64_t db_lo = make_smem_desc(b_lo + ko, p.sbo_bytes, p.layout_type);
+            // descriptor low words (start address >> 4); a k-step of 16 bf16 = 32 B = +2
+            const uint32_t a_hi = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes));
+            const uint32_t a_lo = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes + p.a_plane_bytes));
+            const uint32_t b_hi = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes));
+            const uint32_t b_lo = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes + p.b_plane_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k >= ksteps) break;
+              const uint32_t ko = (uint32_t)(2 * k);
               if (elect_one_sync()) {
-                umma_bf16(d_tmem, da_hi, db_hi, p.idesc, accumulate);
-                umma_bf16(d_tmem, da_lo, db_hi, p.idesc, 1u);
-                umma_bf16(d_tmem, da_hi, db_lo, p.idesc, 1u);
+                umma_bf16_w(d_tmem, a_hi + ko, b_hi + ko, dhi, p.idesc, accumulate);
+                umma_bf16_w(d_tmem, a_lo + ko, b_hi + ko, dhi, p.idesc, 1u);
+                umma_bf16_w(d_tmem, a_hi + ko, b_lo + ko, dhi, p.idesc, 1u);
               }
               accumulate = 1u;
             }

@@ -264,7 +264,7 @@ bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err) {
 }
 
 bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out) {
-  if (!tc.flat.ok || g_tc_debug[3]) return false;
+  if (!tc.flat.ok || g_tc_debug[3] != 1) return false;   // experimental: opt-in (VR_FLAT=1), see DESIGN.md
   if (L.k != 3 || L.stride != 1) return false;
   if (out.W > 64 || in.W != out.W || in.H != out.H) return false;
   if (in.sh % in.sw) return false;

@@ -3,6 +3,7 @@
 // inference.py:42-68 (_separate) -> lib/nets.py:124-131 (predict_mask) -> lib/nets.py:82-117 (forward)
 // -> lib/nets.py:26-41 (BaseNet) -> lib/layers.py.
 #include "engine.h"
+#include "tc_plan.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -201,7 +202,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   // Feature maps that feed a 3x3 stride-1 convolution at W <= 64 carry zero pad pixels after every row (>= the
   // horizontal dilation of their consumers: 1, or 6 for the ASPP input) so that the flat-halo kernel can read the
   // taps as shifted views of one contiguous pixel segment.
-  const int pw = (W / 4 <= 64) ? 2 : 0;
+  const int pw = (g_tc_debug[3] == 1 && W / 4 <= 64) ? 2 : 0;   // only when the (experimental) flat kernel is enabled
   P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n, pw);
   P.cat3 = make_buffer(Nb, H / 4, W / 4, 10 * n, pw);
   P.t4 = make_buffer(Nb, H / 8, W / 8, 6 * n, pw);
@@ -763,7 +764,7 @@ bool Engine::debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   std::vector<void*> tmp;
   std::swap(tmp, allocs_);
-  Buffer bin = make_buffer(N, H, W, cin_pad, W <= 64 ? (dil_w > 2 ? dil_w : 2) : 0);   // pad pixels: flat-halo kernel
+  Buffer bin = make_buffer(N, H, W, cin_pad, (g_tc_debug[3] == 1 && W <= 64) ? (dil_w > 2 ? dil_w : 2) : 0);
   Buffer bout = make_buffer(N, Ho, Wo, round_up(Cout, 8));
   ConvLayer L;
   L.name = "debug_conv";

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -32,7 +33,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Spin on an mbarrier phase.  Kept to the bare try_wait loop: measured on B200, adding a poll counter + trap
+// (either in C++ or inside the asm, even though only on the failure path) costs ~5 % of the convolution
+// throughput.  -DVR_WAIT_TIMEOUT builds the trapping variant for bring-up of new pipelines (a barrier bug then
+// aborts the kernel after ~2^28 polls instead of hanging the GPU).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef VR_WAIT_TIMEOUT
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 q, n, 0x10000000;\n\t"
+      "@q bra WAIT_LOOP;\n\t"
+      "trap;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -44,6 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");
+#endif
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvr_b200.so')
+LIB_PATH = os.environ.get('VR_LIB_PATH', os.path.join(os.path.dirname(_HERE), 'libvr_b200.so'))
 
 c_i32, c_i64, c_vp, c_fp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p
 
@@ -72,6 +72,8 @@ def load_library():
     # validation knobs of the tensor-core kernels (see vr_debug_set in include/vr_b200.h)
     if os.environ.get('VR_ROWS_KB'):
         lib.vr_debug_set(2, int(os.environ['VR_ROWS_KB']))
+    if os.environ.get('VR_FLAT'):
+        lib.vr_debug_set(3, int(os.environ['VR_FLAT']))
     if os.environ.get('VR_NO_ROWS'):
         lib.vr_debug_set(1, int(os.environ['VR_NO_ROWS']))
     _lib = lib
