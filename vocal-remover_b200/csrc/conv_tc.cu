@@ -148,26 +148,28 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const int nsub = min(p.SUBS, p.total_sub - it * p.SUBS);
           const uint32_t sbase = smem_base + (uint32_t)(stage * stage_bytes);
-          for (int j = 0; j < nsub; ++j) {
-            // descriptor low words (start address >> 4); a k-step of 16 bf16 = 32 B = +2
-            const uint32_t a_hi = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes));
-            const uint32_t a_lo = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes + p.a_plane_bytes));
-            const uint32_t b_hi = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes));
-            const uint32_t b_lo = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes + p.b_plane_bytes));
+          // one elected lane issues the whole stage (ptxas keeps the region branch-free after elect.sync)
+          if (elect_one_sync()) {
+            for (int j = 0; j < nsub; ++j) {
+              // descriptor low words (start address >> 4); a k-step of 16 bf16 = 32 B = +2
+              const uint32_t a_hi = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes));
+              const uint32_t a_lo = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes + p.a_plane_bytes));
+              const uint32_t b_hi = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes));
+              const uint32_t b_lo = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes + p.b_plane_bytes));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k >= ksteps) break;
-              const uint32_t ko = (uint32_t)(2 * k);
-              if (elect_one_sync()) {
+              for (int k = 0; k < 4; ++k) {
+                if (k >= ksteps) break;
+                const uint32_t ko = (uint32_t)(2 * k);
                 umma_bf16_w(d_tmem, a_hi + ko, b_hi + ko, dhi, p.idesc, accumulate);
                 umma_bf16_w(d_tmem, a_lo + ko, b_hi + ko, dhi, p.idesc, 1u);
                 umma_bf16_w(d_tmem, a_hi + ko, b_lo + ko, dhi, p.idesc, 1u);
+                accumulate = 1u;
               }
-              accumulate = 1u;
             }
+            umma_commit(smem_u32(&bar_empty[stage]));   // frees the slot once the MMAs have read it
           }
+          accumulate = 1u;
           __syncwarp();
-          if (elect_one_sync()) umma_commit(smem_u32(&bar_empty[stage]));   // frees the slot once the MMAs have read it
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;

@@ -167,22 +167,22 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN) * row_bytes;
             const uint32_t idesc_all = p.idesc0 | ((uint32_t)((cnt * p.BN) >> 3) << 17);
             const bool fresh = cc == 0 && r <= kR - 1;   // accumulator r receives its first product now
+            if (elect_one_sync()) {   // one elected lane issues the whole row
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t bk_hi = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b_row0);
-              const uint32_t bk_lo = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b3_plane + b_row0);
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t bk_hi = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b_row0);
+                const uint32_t bk_lo = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b3_plane + b_row0);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks >= p.ksteps) break;
-                const uint32_t ao = ((uint32_t)kw * row_bytes + (uint32_t)(ks * 32)) >> 4;
-                const uint32_t ko = (uint32_t)((ks * 32) >> 4);
-                if (kw == 0 && ks == 0 && fresh) {
-                  // first touch of accumulator r must overwrite: split the stacked MMA once
-                  const uint32_t n_old = (uint32_t)((cnt - 1) * p.BN);
-                  const uint32_t idesc_old = p.idesc0 | ((n_old >> 3) << 17);
-                  const uint32_t idesc_new = p.idesc0 | ((uint32_t)(p.BN >> 3) << 17);
-                  const uint32_t bn_off = ((uint32_t)((cnt - 1) * p.BN) * row_bytes) >> 4;
-                  if (elect_one_sync()) {
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks >= p.ksteps) break;
+                  const uint32_t ao = ((uint32_t)kw * row_bytes + (uint32_t)(ks * 32)) >> 4;
+                  const uint32_t ko = (uint32_t)((ks * 32) >> 4);
+                  if (kw == 0 && ks == 0 && fresh) {
+                    // first touch of accumulator r must overwrite: split the stacked MMA once
+                    const uint32_t n_old = (uint32_t)((cnt - 1) * p.BN);
+                    const uint32_t idesc_old = p.idesc0 | ((n_old >> 3) << 17);
+                    const uint32_t idesc_new = p.idesc0 | ((uint32_t)(p.BN >> 3) << 17);
+                    const uint32_t bn_off = ((uint32_t)((cnt - 1) * p.BN) * row_bytes) >> 4;
                     if (cnt > 1) {
                       umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_old, 1u);
                       umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_old, 1u);
@@ -191,18 +191,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
                     umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_hi + ko + bn_off, dhi, idesc_new, 0u);
                     umma_bf16_w(d_tmem + n_old, a_lo + ao, bk_hi + ko + bn_off, dhi, idesc_new, 1u);
                     umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_lo + ko + bn_off, dhi, idesc_new, 1u);
-                  }
-                } else {
-                  if (elect_one_sync()) {
+                  } else {
                     umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_all, 1u);
                     umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_all, 1u);
                     umma_bf16_w(d_tmem, a_hi + ao, bk_lo + ko, dhi, idesc_all, 1u);
                   }
                 }
               }
+              umma_commit(smem_u32(&bar_aempty[as]));
             }
             __syncwarp();
-            if (elect_one_sync()) umma_commit(smem_u32(&bar_aempty[as]));
             if (++as == p.n_aslots) {
               as = 0;
               aph ^= 1u;
