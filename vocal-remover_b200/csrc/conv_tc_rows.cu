@@ -27,12 +27,12 @@
 namespace vr {
 
 static constexpr int kRowsThreads = 192;
-static constexpr int kR = 8;                       // output rows per CTA tile
+static constexpr int kMaxR = 8;                    // output rows per CTA tile (runtime: 8, or 4 with two CTAs per SM)
 static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
 static constexpr int kMaxASlots = 8;
 
 struct RowsParams {
-  int N, H, W, tiles_w, tiles_h, n_tiles, total_tiles;
+  int N, H, W, R, tiles_w, tiles_h, n_tiles, total_tiles;
   int chunks, CinPadR, BN, Cout, act;
   int KB, ksteps, a_plane, a_slot, n_aslots, sbo, layout;   // channel-chunk width 64 (SW128) or 32 (SW64)
   int b_kw_bytes, b_buf_bytes;
@@ -46,7 +46,7 @@ struct RowsParams {
   int bo_mode;
 };
 
-__global__ void __launch_bounds__(kRowsThreads, 1)
+__global__ void __launch_bounds__(kRowsThreads, 2)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         int mt = tile / p.n_tiles;
         const int w0 = (mt % p.tiles_w) * 128;
         mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * kR;
+        const int h0 = (mt % p.tiles_h) * p.R;
         const int n = mt / p.tiles_h;
         for (int cc = 0; cc < p.chunks; ++cc) {
           mbar_wait(smem_u32(&bar_bempty[bs]), bph ^ 1u);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             bs = 0;
             bph ^= 1u;
           }
-          for (int r = 0; r < kR + 2; ++r) {
+          for (int r = 0; r < p.R + 2; ++r) {
             mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
             const uint32_t afull = smem_u32(&bar_afull[as]);
             const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
@@ -149,24 +149,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_set = tmem_base + (uint32_t)(acc * kR * p.BN);
+        const uint32_t d_set = tmem_base + (uint32_t)(acc * p.R * p.BN);
         for (int cc = 0; cc < p.chunks; ++cc) {
           mbar_wait(smem_u32(&bar_bfull[bs]), bph);
           const uint32_t bsrc = b_base + (uint32_t)(bs * p.b_buf_bytes);
-          for (int r = 0; r < kR + 2; ++r) {
+          for (int r = 0; r < p.R + 2; ++r) {
             mbar_wait(smem_u32(&bar_afull[as]), aph);
             tc_fence_after();
             const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * p.a_slot));
             const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * p.a_slot + p.a_plane));
             // input row r feeds output rows o = r-kh; accumulators o_lo..o_hi are adjacent TMEM column blocks
             const int o_lo = r - 2 < 0 ? 0 : r - 2;
-            const int o_hi = r > kR - 1 ? kR - 1 : r;
+            const int o_hi = r > p.R - 1 ? p.R - 1 : r;
             const int cnt = o_hi - o_lo + 1;
             const uint32_t d_tmem = d_set + (uint32_t)(o_lo * p.BN);
             // weight rows are stacked [kh=2 | kh=1 | kh=0]; block of accumulator o_lo is kh = r - o_lo
             const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN) * row_bytes;
             const uint32_t idesc_all = p.idesc0 | ((uint32_t)((cnt * p.BN) >> 3) << 17);
-            const bool fresh = cc == 0 && r <= kR - 1;   // accumulator r receives its first product now
+            const bool fresh = cc == 0 && r <= p.R - 1;   // accumulator r receives its first product now
             if (elect_one_sync()) {   // one elected lane issues the whole row
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
@@ -231,14 +231,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       int mt = tile / p.n_tiles;
       const int w0 = (mt % p.tiles_w) * 128;
       mt /= p.tiles_w;
-      const int h0 = (mt % p.tiles_h) * kR;
+      const int h0 = (mt % p.tiles_h) * p.R;
       const int n = mt / p.tiles_h;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t t_set = tmem_base + (uint32_t)(acc * kR * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int orow = 0; orow < kR; ++orow) {
+      const uint32_t t_set = tmem_base + (uint32_t)(acc * p.R * p.BN) + ((uint32_t)(q * 32) << 16);
+      for (int orow = 0; orow < p.R; ++orow) {
         const int64_t obase = (int64_t)n * p.osn + (int64_t)(h0 + orow) * p.osh + (int64_t)(w0 + px) * p.osw;
-        const bool last_row = orow == kR - 1;
+        const bool last_row = orow == p.R - 1;
         if (p.BN == 32) {
           float v[32];
           tmem_ld32(t_set + (uint32_t)(orow * 32), v);
@@ -338,7 +338,7 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out) {
   if (!tc.rows.ok || g_tc_debug[1]) return false;
   if (L.k != 3 || L.stride != 1 || L.dil_h != 1 || L.dil_w != 1) return false;
-  if (out.W % 128 || out.H % kR || in.H != out.H || in.W != out.W) return false;
+  if (out.W % 128 || out.H % kMaxR || in.H != out.H || in.W != out.W) return false;
   if (in.sw % 8 || in.sh % 8 || in.sn % 8) return false;
   if ((reinterpret_cast<uintptr_t>(in.hi) | reinterpret_cast<uintptr_t>(in.lo)) & 15) return false;
   return true;
@@ -372,7 +372,11 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   }
   RowsParams p;
   p.N = out.N; p.H = out.H; p.W = out.W;
-  p.tiles_w = out.W / 128; p.tiles_h = out.H / kR; p.n_tiles = R.n_tiles;
+  // g_tc_debug[4] = 1: two CTAs per SM (4 rows per tile, 32-channel chunks, 2 row slots, <= 256 TMEM columns each)
+  // so that two MMA-issuing threads feed the tensor pipe; needs the 32-channel chunk layout
+  const bool dual = g_tc_debug[4] == 1 && R.KB == 32;
+  p.R = dual ? 4 : kMaxR;
+  p.tiles_w = out.W / 128; p.tiles_h = out.H / p.R; p.n_tiles = R.n_tiles;
   p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
   p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.BN = R.BN; p.Cout = L.Cout; p.act = L.act;
   p.KB = R.KB; p.ksteps = R.KB / 16;
@@ -386,7 +390,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.out_hi = out.hi; p.out_lo = out.lo;
   p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
   p.bias = R.bias;
-  p.tmem_cols = 2 * kR * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
+  p.tmem_cols = 2 * p.R * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
   p.bo_mode = g_tc_debug[0];
   static bool attr_set = false;
   static int num_sms = 0, max_smem = 0;
@@ -396,16 +400,19 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048);
+    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
   p.n_aslots = (max_smem - 2048 - 1024 - 2 * p.b_buf_bytes) / p.a_slot;
   if (p.n_aslots > kMaxASlots) p.n_aslots = kMaxASlots;
+  if (dual) p.n_aslots = 2;
   if (p.n_aslots < 2) {
     err = "tc_rows_launch: shared memory too small";
     return cudaErrorInvalidValue;
   }
   const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + 1024;
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const int ctas = dual ? 2 * num_sms : num_sms;
+  const int grid = p.total_tiles < ctas ? p.total_tiles : ctas;
   conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, p);
   return cudaGetLastError();
 }

@@ -74,6 +74,8 @@ def load_library():
         lib.vr_debug_set(2, int(os.environ['VR_ROWS_KB']))
     if os.environ.get('VR_FLAT'):
         lib.vr_debug_set(3, int(os.environ['VR_FLAT']))
+    if os.environ.get('VR_ROWS_DUAL'):
+        lib.vr_debug_set(4, int(os.environ['VR_ROWS_DUAL']))
     if os.environ.get('VR_NO_ROWS'):
         lib.vr_debug_set(1, int(os.environ['VR_NO_ROWS']))
     _lib = lib
