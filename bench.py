@@ -36,6 +36,9 @@ UNIT = 'audio-s/s'
 SR = 44100
 SECONDS_PER_GPU = 240.0
 CONV_FLOP_PER_WINDOW = 135.714e9
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 97 convolution launches of one 8-window forward, / 8
+# (ncu capture profiles/r01_launches_bench30s_final.csv); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
+CONV_DRAM_BYTES_PER_WINDOW = 1.225e9
 
 
 def measured_peaks():
@@ -245,7 +248,10 @@ def run_gpu(args):
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'kernel': 'conv_tc_rows_kernel + conv_tc_flat_kernel + conv_tc_kernel (tcgen05 implicit-GEMM conv family, '
                           'bf16x3 split precision)',
-                'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+                'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+                'traffic': CONV_DRAM_BYTES_PER_WINDOW * n_windows / world / max(1.0, tc_n),
+                'traffic_note': 'average DRAM bytes per convolution launch = 1.225 GB per window (ncu, '
+                                'profiles/r01_launches_bench30s_final.csv) x windows per rank / launches',
                 'peak_source': peak_src,
                 'note': 'achieved = algorithmic conv FLOPs (real channel counts, 1x per product; the kernel issues 3 '
                         'bf16 MMA passes per product) of %d launches / their summed CUDA-event time %.2f ms on rank '

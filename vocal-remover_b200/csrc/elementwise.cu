@@ -79,6 +79,7 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 // One thread per (output pixel, 8-channel chunk); grid.y = (image, output row) so all per-thread index math is
 // 32-bit with one division.  Source index and weights follow ATen's upsample_bilinear2d with
 // align_corners=True: scale = (in-1)/(out-1) in fp32, src = scale*dst.
+template <int CH>   // channels per thread: 8 (one 16-byte access per plane) or 16 (32 bytes: STG.256, twice the loads in flight)
 __global__ void __launch_bounds__(256) upsample2x_kernel(ActView in, ActView out, int chunks, float sh, float sw) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= out.W * chunks) return;
@@ -91,34 +92,52 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(ActView in, ActView out
   const int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
   const float ly = fy - y0, lx = fx - x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const int64_t base = (int64_t)n * in.sn + ck * 8;
+  const int64_t base = (int64_t)n * in.sn + ck * CH;
   const int64_t r0 = base + (int64_t)y0 * in.sh, r1 = base + (int64_t)y1 * in.sh;
   const int c0 = x0 * in.sw, c1 = x1 * in.sw;
-  const bf16x8 ah = ld128(in.hi + r0 + c0), al = ld128(in.lo + r0 + c0);
-  const bf16x8 bh = ld128(in.hi + r0 + c1), bl = ld128(in.lo + r0 + c1);
-  const bf16x8 ch = ld128(in.hi + r1 + c0), cl = ld128(in.lo + r1 + c0);
-  const bf16x8 dh = ld128(in.hi + r1 + c1), dl = ld128(in.lo + r1 + c1);
-  float a[8], b[8], c[8], d[8], y[8];
-  unpack8(ah, al, a);
-  unpack8(bh, bl, b);
-  unpack8(ch, cl, c);
-  unpack8(dh, dl, d);
+  constexpr int V = CH / 8;
+  bf16x8 ah[V], al[V], bh[V], bl[V], ch[V], cl[V], dh[V], dl[V];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-  const int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * 8;
-  bf16x8 h, l;
-  split8(y, h, l);
-  st128(out.hi + oo, h);
-  st128(out.lo + oo, l);
+  for (int v = 0; v < V; ++v) {
+    ah[v] = ld128(in.hi + r0 + c0 + 8 * v); al[v] = ld128(in.lo + r0 + c0 + 8 * v);
+    bh[v] = ld128(in.hi + r0 + c1 + 8 * v); bl[v] = ld128(in.lo + r0 + c1 + 8 * v);
+    ch[v] = ld128(in.hi + r1 + c0 + 8 * v); cl[v] = ld128(in.lo + r1 + c0 + 8 * v);
+    dh[v] = ld128(in.hi + r1 + c1 + 8 * v); dl[v] = ld128(in.lo + r1 + c1 + 8 * v);
+  }
+  const int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw + ck * CH;
+  bf16x8 h[V], l[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float a[8], b[8], c[8], d[8], y[8];
+    unpack8(ah[v], al[v], a);
+    unpack8(bh[v], bl[v], b);
+    unpack8(ch[v], cl[v], c);
+    unpack8(dh[v], dl[v], d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+    split8(y, h[v], l[v]);
+  }
+  if (V == 2) {
+    st256(out.hi + oo, h[0], h[V - 1]);
+    st256(out.lo + oo, l[0], l[V - 1]);
+  } else {
+    st128(out.hi + oo, h[0]);
+    st128(out.lo + oo, l[0]);
+  }
 }
 
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
-  const int chunks = in.C >> 3;
-  if ((int64_t)out.N * out.H * out.W * chunks == 0) return cudaSuccess;
+  if ((int64_t)out.N * out.H * out.W * (in.C >> 3) == 0) return cudaSuccess;
   const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
   const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  const bool wide = in.C % 16 == 0 && out.sw % 16 == 0 && in.sw % 16 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo)) & 31) == 0;
+  const int chunks = wide ? in.C >> 4 : in.C >> 3;
   dim3 grid((unsigned)ceil_div(out.W * chunks, 256), (unsigned)(out.N * out.H));
-  upsample2x_kernel<<<grid, 256, 0, stream>>>(in, out, chunks, sh, sw);
+  if (wide)
+    upsample2x_kernel<16><<<grid, 256, 0, stream>>>(in, out, chunks, sh, sw);
+  else
+    upsample2x_kernel<8><<<grid, 256, 0, stream>>>(in, out, chunks, sh, sw);
   return cudaGetLastError();
 }
 

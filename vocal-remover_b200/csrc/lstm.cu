@@ -109,12 +109,18 @@ __global__ void __launch_bounds__(4 * HID) lstm_recurrence_kernel(const float* _
   int t = dir ? T - 1 : 0;
   float xnext = xp_n[(int64_t)t * 8 * HID];
   for (int s = 0; s < T; ++s) {
-    float g = xnext;
     const int tn = dir ? t - 1 : t + 1;
+    // four independent partial sums: the 4-cycle FMA latency chain is HID/4 long instead of HID
+    float g0 = xnext, g1 = 0.f, g2 = 0.f, g3 = 0.f;
     if (s + 1 < T) xnext = xp_n[(int64_t)tn * 8 * HID];
 #pragma unroll
-    for (int k = 0; k < HID; ++k) g = fmaf(wrow[k], h_s[k], g);
-    g_s[j] = g;
+    for (int k = 0; k < HID; k += 4) {
+      g0 = fmaf(wrow[k], h_s[k], g0);
+      g1 = fmaf(wrow[k + 1], h_s[k + 1], g1);
+      g2 = fmaf(wrow[k + 2], h_s[k + 2], g2);
+      g3 = fmaf(wrow[k + 3], h_s[k + 3], g3);
+    }
+    g_s[j] = (g0 + g1) + (g2 + g3);
     __syncthreads();
     if (j < HID) {
       float ig = sigmoid_acc(g_s[j]);
