@@ -35,7 +35,8 @@ struct TcParams {
   int stride, pad_h, pad_w, dil_h, dil_w, KW;
   int KB, cchunks, SUBS, total_sub, CinPadTC, BN, Cout, act, stages;
   int a_sub_bytes, b_sub_bytes, a_plane_bytes, b_plane_bytes;
-  uint32_t idesc;
+  uint32_t idesc;    // N = BN
+  uint32_t idesc2;   // N = 2*BN: one MMA against the stacked [B_hi ; B_lo] planes
   uint32_t sbo_bytes, layout_type;
   bf16* out_hi;
   bf16* out_lo;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.BN);   // [D1 | D2], see the issue loop
         uint32_t accumulate = 0;
         for (int it = 0; it < num_iters; ++it) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
@@ -155,14 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint32_t a_hi = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes));
               const uint32_t a_lo = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes + p.a_plane_bytes));
               const uint32_t b_hi = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes));
-              const uint32_t b_lo = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes + p.b_plane_bytes));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (k >= ksteps) break;
                 const uint32_t ko = (uint32_t)(2 * k);
-                umma_bf16_w(d_tmem, a_hi + ko, b_hi + ko, dhi, p.idesc, accumulate);
+                // The hi and lo weight planes are adjacent in the stage ([BN rows hi][BN rows lo], same pitch), so
+                // A_hi meets both in ONE N = 2*BN instruction: D1 += A_hi*B_hi, D2 += A_hi*B_lo.  A second
+                // N = BN instruction adds A_lo*B_hi to D1.  Two instructions and one shared-memory pass over A_hi
+                // per k-step instead of three; the epilogue adds D1 + D2.
+                umma_bf16_w(d_tmem, a_hi + ko, b_hi + ko, dhi, p.idesc2, accumulate);
                 umma_bf16_w(d_tmem, a_lo + ko, b_hi + ko, dhi, p.idesc, 1u);
-                umma_bf16_w(d_tmem, a_hi + ko, b_lo + ko, dhi, p.idesc, 1u);
                 accumulate = 1u;
               }
             }
@@ -203,11 +206,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t obase = (int64_t)n * p.osn + (int64_t)(h0 + dh) * p.osh + (int64_t)(w0 + dw) * p.osw;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * 2 * p.BN) + ((uint32_t)(q * 32) << 16);
       int c0 = 0;
       for (; c0 + 32 <= p.BN; c0 += 32) {
-        float v[32];
+        float v[32], v2[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
+        tmem_ld32(t_row + (uint32_t)(p.BN + c0), v2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[i];
         if (c0 + 32 >= p.BN) {   // all of this warp's TMEM reads are done: hand the accumulator back
           tc_fence_before();
           __syncwarp();
@@ -216,8 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (valid) epilogue_store<2>(v, bias_s, nt * p.BN + c0, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
       }
       if (c0 < p.BN) {   // BN is a multiple of 16: one trailing 16-column group
-        float v[16];
+        float v[16], v2[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld16(t_row + (uint32_t)(p.BN + c0), v2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += v2[i];
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
@@ -429,13 +438,14 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
   // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * tc.BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.sbo_bytes = (uint32_t)(8 * tc.KB * 2);
   p.layout_type = tc.KB == 64 ? 2u : tc.KB == 32 ? 4u : 6u;
   p.out_hi = out.hi; p.out_lo = out.lo;
   p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
   p.bias = tc.bias;
   int cols = 32;
-  while (cols < 2 * tc.BN) cols <<= 1;
+  while (cols < 4 * tc.BN) cols <<= 1;   // two accumulators x [D1 | D2]
   p.tmem_cols = cols;
   static int num_sms = 0;
   if (!num_sms) {
