@@ -92,6 +92,13 @@ VR_API int vr_separate(vr_ctx* ctx, const void* spec, int64_t T, int32_t tta, fl
 VR_API int vr_apply_mask(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, void* y_spec, void* v_spec,
                   void* stream);
 
+/* --postprocess / spec_utils.merge_artifacts (lib/spec_utils.py:60-93, inference.py:27-30) without moving the mask
+ * off the device: frame_min[t] = min over (channel, bin) of mask[:, :, t] (device float[T]); the caller finds the
+ * long above-threshold runs on the host from those T floats (lib/spec_utils.py:artifact_weights) and hands back one
+ * fade weight per frame, which vr_mask_apply_weight applies in place: mask += weight[t] * (1 - mask).           */
+VR_API int vr_mask_frame_min(vr_ctx* ctx, const float* mask, int64_t T, float* frame_min, void* stream);
+VR_API int vr_mask_apply_weight(vr_ctx* ctx, float* mask, int64_t T, const float* weight, void* stream);
+
 /* y/v waves straight from spec and mask: _postprocess + 2x spectrogram_to_wave fused
  * (inference.py:32-36,171,176).  wave_inst / wave_voc: [2][hop*(T-1)].                                 */
 VR_API int vr_apply_mask_istft(vr_ctx* ctx, const void* spec, const float* mask, int64_t T, float* wave_inst,

@@ -301,3 +301,34 @@ def test_full_size_track_properties(default_model):
     # identical here (same sine mix amplitude): compare the first two windows' worth of samples with the oracle
     assert torch.isfinite(inst).all() and torch.isfinite(voc).all()
     assert inst.abs().max().item() <= 1.5 * float(np.abs(wave).max())
+
+
+def test_postprocess_device_matches_host_merge_artifacts(default_model):
+    """--postprocess: device frame-min + weight apply == the host merge_artifacts (which tests/test_host_logic.py
+    pins against the reference's lib/spec_utils.py:60-93)."""
+    import inference
+    from lib import _native, spec_utils
+    rng = np.random.default_rng(5)
+    T = 700
+    m = rng.uniform(0.0, 0.04, size=(2, 1025, T)).astype(np.float32)
+    for s, e in ((0, 90), (200, 330), (340, 500), (640, 700)):
+        m[:, :, s:e] = rng.uniform(0.06, 1.0, size=(2, 1025, e - s))
+    ref = spec_utils.merge_artifacts(m.copy())
+    sp = inference.Separator(default_model, _dev(), 4, 256, True)
+    ctx = sp._ctx()
+    d_mask = torch.from_numpy(m).cuda()
+    fmin = torch.empty(T, dtype=torch.float32, device='cuda')
+    ctx.check(ctx.lib.vr_mask_frame_min(ctx.handle, _native.ptr(d_mask), T, _native.ptr(fmin), _native.stream_ptr()),
+              'vr_mask_frame_min')
+    assert np.array_equal(fmin.cpu().numpy(), m.min(axis=(0, 1)))
+    w = torch.from_numpy(spec_utils.artifact_weights(fmin.cpu().numpy())).cuda()
+    assert float(w.max()) == 1.0 and float(w.min()) == 0.0
+    ctx.check(ctx.lib.vr_mask_apply_weight(ctx.handle, _native.ptr(d_mask), T, _native.ptr(w), _native.stream_ptr()),
+              'vr_mask_apply_weight')
+    assert np.abs(d_mask.cpu().numpy() - ref).max() < 1e-6
+    # and the flag is wired through the Separator (no long above-threshold run in this track: identical result)
+    from lib import synth
+    wave = synth.sine_mix(4.0)
+    a = sp.separate_wave(wave)[0]
+    b = inference.Separator(default_model, _dev(), 4, 256, False).separate_wave(wave)[0]
+    assert np.abs(a - b).max() < 1e-6

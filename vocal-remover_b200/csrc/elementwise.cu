@@ -364,6 +364,38 @@ cudaError_t launch_lexmax_abs(const float2* spec, int64_t n, unsigned long long*
   return cudaGetLastError();
 }
 
+// --postprocess (reference lib/spec_utils.py:60-93, inference.py:27-30) on the device: the per-frame minimum of the
+// mask over (channel, bin) goes to the host (4 B per frame), which finds the long above-threshold runs exactly as the
+// reference does and returns one fade weight per frame; the mask is then pulled towards 1 by that weight.
+__global__ void mask_frame_min_kernel(const float* __restrict__ mask, int rows, int64_t T, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float m = mask[t];
+  for (int r = 1; r < rows; ++r) m = fminf(m, mask[(int64_t)r * T + t]);
+  out[t] = m;
+}
+
+cudaError_t launch_mask_frame_min(const float* mask, int rows, int64_t T, float* out, cudaStream_t stream) {
+  if (T == 0) return cudaSuccess;
+  mask_frame_min_kernel<<<(unsigned)((T + 127) / 128), 128, 0, stream>>>(mask, rows, T, out);
+  return cudaGetLastError();
+}
+
+__global__ void mask_apply_weight_kernel(float* __restrict__ mask, int64_t n, int64_t T,
+                                         const float* __restrict__ weight) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float m = mask[i];
+  mask[i] = m + weight[i % T] * (1.f - m);
+}
+
+cudaError_t launch_mask_apply_weight(float* mask, int rows, int64_t T, const float* weight, cudaStream_t stream) {
+  const int64_t n = (int64_t)rows * T;
+  if (n == 0) return cudaSuccess;
+  mask_apply_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(mask, n, T, weight);
+  return cudaGetLastError();
+}
+
 __global__ void apply_mask_kernel(const float2* __restrict__ spec, const float* __restrict__ mask, int64_t n,
                                   float2* __restrict__ y, float2* __restrict__ v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

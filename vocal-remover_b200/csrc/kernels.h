@@ -41,6 +41,8 @@ cudaError_t launch_absmax_range(const float2* spec, int nrows, int64_t T, int64_
                                 cudaStream_t stream);
 cudaError_t launch_lexmax_abs(const float2* spec, int64_t n, unsigned long long* scratch, float* out_norm,
                               cudaStream_t stream);
+cudaError_t launch_mask_frame_min(const float* mask, int rows, int64_t T, float* out, cudaStream_t stream);
+cudaError_t launch_mask_apply_weight(float* mask, int rows, int64_t T, const float* weight, cudaStream_t stream);
 cudaError_t launch_apply_mask(const float2* spec, const float* mask, int64_t n, float2* y, float2* v,
                               cudaStream_t stream);
 

@@ -52,9 +52,14 @@ class Separator(object):
         ctx.check(ctx.lib.vr_separate(ctx.handle, _native.ptr(d_spec), T, 1 if tta else 0, _native.ptr(d_mask),
                                       _native.stream_ptr()), 'vr_separate')
         if self.postprocess:
-            # --postprocess stays on the host for now
-            m = spec_utils.merge_artifacts(d_mask.cpu().numpy())
-            d_mask = torch.from_numpy(m).to(d_spec.device)
+            # --postprocess (inference.py:27-30): only T floats leave the device, the run detection of
+            # merge_artifacts runs on the host, the fade weights are applied on the device
+            frame_min = torch.empty(T, dtype=torch.float32, device=d_spec.device)
+            ctx.check(ctx.lib.vr_mask_frame_min(ctx.handle, _native.ptr(d_mask), T, _native.ptr(frame_min),
+                                                _native.stream_ptr()), 'vr_mask_frame_min')
+            weight = torch.from_numpy(spec_utils.artifact_weights(frame_min.cpu().numpy())).to(d_spec.device)
+            ctx.check(ctx.lib.vr_mask_apply_weight(ctx.handle, _native.ptr(d_mask), T, _native.ptr(weight),
+                                                   _native.stream_ptr()), 'vr_mask_apply_weight')
         return d_mask
 
     def _run(self, X_spec, tta):
@@ -102,13 +107,27 @@ class Separator(object):
         (inference.py:147,158-161,171,176) without leaving the GPU in between.  ``wave`` may be a numpy
         array (host; copied in and out) or a CUDA tensor (returns CUDA tensors).
         """
-        if self.postprocess:
-            X = spec_utils.wave_to_spectrogram(np.asarray(wave.cpu() if torch.is_tensor(wave) else wave),
-                                               self.model.hop_length, self.model.n_fft)
-            y, v = self._run(X, tta)
-            return (spec_utils.spectrogram_to_wave(y, self.model.hop_length),
-                    spec_utils.spectrogram_to_wave(v, self.model.hop_length))
         ctx = self._ctx()
+        if self.postprocess:
+            # staged on the device: STFT -> mask (+ postprocess) -> masked inverse STFT
+            dev = self._dev()
+            hop, n_fft = self.model.hop_length, self.model.n_fft
+            with torch.cuda.device(dev):
+                host = not (torch.is_tensor(wave) and wave.is_cuda)
+                w = (torch.from_numpy(np.ascontiguousarray(np.asarray(wave, dtype=np.float32))).to(dev) if host
+                     else wave.contiguous().float())
+                L = w.shape[1]
+                T = 1 + L // hop
+                d_spec = torch.empty((2, n_fft // 2 + 1, T), dtype=torch.complex64, device=dev)
+                ctx.check(ctx.lib.vr_stft(ctx.handle, _native.ptr(w), L, _native.ptr(d_spec), T, None,
+                                          _native.stream_ptr()), 'vr_stft')
+                d_mask = self._mask_device(d_spec, tta)
+                inst = torch.empty((2, hop * (T - 1)), dtype=torch.float32, device=dev)
+                voc = torch.empty_like(inst)
+                ctx.check(ctx.lib.vr_apply_mask_istft(ctx.handle, _native.ptr(d_spec), _native.ptr(d_mask), T,
+                                                      _native.ptr(inst), _native.ptr(voc), _native.stream_ptr()),
+                          'vr_apply_mask_istft')
+                return (inst.cpu().numpy(), voc.cpu().numpy()) if host else (inst, voc)
         dev = self._dev()
         hop = self.model.hop_length
         with torch.cuda.device(dev):

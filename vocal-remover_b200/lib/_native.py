@@ -34,6 +34,8 @@ SIGNATURES = {
     'vr_separate_windows': (c_i32, [c_vp, c_vp, c_i64, c_fp, c_i32, c_i32, c_i32, c_fp, c_i64, c_i64, c_i32, c_vp]),
     'vr_separate': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_fp, c_vp]),
     'vr_apply_mask': (c_i32, [c_vp, c_vp, c_fp, c_i64, c_vp, c_vp, c_vp]),
+    'vr_mask_frame_min': (c_i32, [c_vp, c_fp, c_i64, c_fp, c_vp]),
+    'vr_mask_apply_weight': (c_i32, [c_vp, c_fp, c_i64, c_fp, c_vp]),
     'vr_apply_mask_istft': (c_i32, [c_vp, c_vp, c_fp, c_i64, c_fp, c_fp, c_vp]),
     'vr_stft_range': (c_i32, [c_vp, c_fp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     'vr_normaliser_range': (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i64, c_fp, c_vp]),

@@ -79,19 +79,19 @@ def spectrogram_to_wave(spec, hop_length=1024):
     return out[0] if mono else out
 
 
-def merge_artifacts(y_mask, thres=0.05, min_range=64, fade_size=32):
-    """``--postprocess`` mask clean-up (reference lib/spec_utils.py:60-93), host-side numpy.
+def artifact_weights(frame_min, thres=0.05, min_range=64, fade_size=32):
+    """Per-frame fade weight of ``merge_artifacts`` from the per-frame minimum of the mask over (channel, bin).
 
-    Frames whose minimum mask value over (channel, bin) exceeds ``thres`` for runs longer than
-    ``min_range`` are treated as vocal-free: the mask is faded towards 1 over them.  SURVEY 8(f)
-    ranks a device version as the next row; the host version keeps the CLI flag working.
+    Frames whose minimum exceeds ``thres`` for runs longer than ``min_range`` are treated as vocal-free; the weight
+    ramps 0 -> 1 over ``fade_size`` frames into such a run and 1 -> 0 out of it (reference lib/spec_utils.py:60-93,
+    including its handling of runs that touch either end of the track or follow each other closely).
     """
     if min_range < fade_size * 2:
         raise ValueError('min_range must be >= fade_size * 2')
-    n_frames = y_mask.shape[2]
-    active = y_mask.min(axis=(0, 1)) > thres
-    idx = np.flatnonzero(active)
-    weight = np.zeros_like(y_mask)
+    frame_min = np.asarray(frame_min)
+    n_frames = frame_min.shape[0]
+    weight = np.zeros(n_frames, dtype=np.float32)
+    idx = np.flatnonzero(frame_min > thres)
     if idx.size:
         breaks = np.flatnonzero(np.diff(idx) != 1)
         starts = np.concatenate([[idx[0]], idx[breaks + 1]])
@@ -104,14 +104,20 @@ def merge_artifacts(y_mask, thres=0.05, min_range=64, fade_size=32):
             if prev_end is not None and s - prev_end < fade_size:
                 s = prev_end - fade_size * 2
             if s != 0:
-                weight[:, :, s:s + fade_size] = np.linspace(0, 1, fade_size)
+                weight[s:s + fade_size] = np.linspace(0, 1, fade_size)
             else:
                 s -= fade_size
             if e != n_frames:
-                weight[:, :, e - fade_size:e] = np.linspace(1, 0, fade_size)
+                weight[e - fade_size:e] = np.linspace(1, 0, fade_size)
             else:
                 e += fade_size
-            weight[:, :, s + fade_size:e - fade_size] = 1
+            weight[s + fade_size:e - fade_size] = 1
             prev_end = e
-    y_mask += weight * (1 - y_mask)
+    return weight
+
+
+def merge_artifacts(y_mask, thres=0.05, min_range=64, fade_size=32):
+    """``--postprocess`` mask clean-up (reference lib/spec_utils.py:60-93) on a host array, in place."""
+    weight = artifact_weights(y_mask.min(axis=(0, 1)), thres, min_range, fade_size)
+    y_mask += weight[None, None, :] * (1 - y_mask)
     return y_mask
