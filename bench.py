@@ -261,7 +261,7 @@ def run_gpu(args):
                                    'tflops': (cc_flops / (cc_ms * 1e-3) / 1e12) if cc_ms > 0 else None}}
     line = None
     if rank == 0:
-        if args.no_cpu_baseline:
+        if args.no_cpu_baseline or world > 1:   # the CPU arm is reported at N=1 only
             cpu_val, cores, secs = None, 0, 0.0
         else:
             cpu_val, cpu_dt, cores, secs = cpu_reference_arm(1, 1, 12.0)
