@@ -69,6 +69,8 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
   cudaStreamCreateWithFlags(&s_hi_, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_lstm_fork_, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ev_lstm_join_, cudaEventDisableTiming);
 }
 
 Engine::~Engine() {
@@ -82,6 +84,8 @@ Engine::~Engine() {
   if (s_hi_) cudaStreamDestroy(s_hi_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
+  if (ev_lstm_fork_) cudaEventDestroy(ev_lstm_fork_);
+  if (ev_lstm_join_) cudaEventDestroy(ev_lstm_join_);
 }
 
 bool Engine::load_tensor(const char* name, int dtype, int ndim, const int64_t* shape, const void* data) {
@@ -463,7 +467,8 @@ bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out,
   return ck(launch_conv_simt(p, s), L.name.c_str());
 }
 
-bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s) {
+bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s,
+                         cudaStream_t side) {
   const int n = P.n, H = P.H;
   // encoders (lib/nets.py:27-31); each skip tensor is written straight into its decoder's concat buffer
   ActView e1 = P.cat1.view(N, 0, H, P.e1_off, n);
@@ -493,19 +498,36 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
   if (!run_conv(P.dec[1], P.cat3.all(N), P.d3.all(N), s)) return false;
   if (!ck(launch_upsample2x(P.d3.all(N), P.cat2.view(N, 0, H / 2, 0, 4 * n), s), "up2")) return false;
   if (!run_conv(P.dec[2], P.cat2.all(N), P.d2.view(N, 0, H / 2, 0, 2 * n), s)) return false;
-  // LSTM branch -> channel 2n of d2 (lib/nets.py:38, lib/layers.py:124-133)
+  // LSTM branch -> channel 2n of d2 (lib/nets.py:38, lib/layers.py:124-133).  Its 128-step recurrence keeps only
+  // 2N CTAs busy, so when a side stream is free (stage 3) it runs there while the main stream upsamples the 2n
+  // convolution channels of d2; only the LSTM channel's 16-channel group is upsampled after the join.
   LstmPlan& Q = P.lstm;
+  const bool overlap = side != nullptr && !profiling_;
+  cudaStream_t sl = overlap ? side : s;
+  if (overlap) {
+    if (!ck(cudaEventRecord(ev_lstm_fork_, s), "lstm fork") || !ck(cudaStreamWaitEvent(side, ev_lstm_fork_, 0), "lstm fork"))
+      return false;
+  }
   launches += 5;
-  if (!ck(launch_lstm_inconv(P.d2.view(N, 0, H / 2, 0, 2 * n), Q.conv_w, Q.conv_bias, Q.l0, s), "lstm conv"))
+  if (!ck(launch_lstm_inconv(P.d2.view(N, 0, H / 2, 0, 2 * n), Q.conv_w, Q.conv_bias, Q.l0, sl), "lstm conv"))
     return false;
-  if (!ck(launch_gemm_nt(Q.l0, Q.wih, Q.bih, Q.xp, N * Q.T, 8 * Q.hid, Q.bins, s), "lstm input projection"))
+  if (!ck(launch_gemm_nt(Q.l0, Q.wih, Q.bih, Q.xp, N * Q.T, 8 * Q.hid, Q.bins, sl), "lstm input projection"))
     return false;
-  if (!ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, s), "lstm recurrence")) return false;
-  if (!ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, P.d2.all(N), 2 * n, s),
+  if (!ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, sl), "lstm recurrence")) return false;
+  if (!ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, P.d2.all(N), 2 * n, sl),
           "lstm dense"))
     return false;
   // dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
-  if (!ck(launch_upsample2x(P.d2.all(N), P.cat1.view(N, 0, H, 0, 2 * n + 16), s), "up1")) return false;
+  if (overlap) {
+    ++launches;
+    if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join")) return false;
+    if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 0, 2 * n), P.cat1.view(N, 0, H, 0, 2 * n), s), "up1")) return false;
+    if (!ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join")) return false;
+    if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 2 * n, 16), P.cat1.view(N, 0, H, 2 * n, 16), s), "up1 lstm"))
+      return false;
+  } else {
+    if (!ck(launch_upsample2x(P.d2.all(N), P.cat1.view(N, 0, H, 0, 2 * n + 16), s), "up1")) return false;
+  }
   return run_conv(P.dec[3], P.cat1.all(N), out, s);
 }
 
@@ -537,7 +559,7 @@ bool Engine::forward(int N, cudaStream_t s) {
       return false;
   }
   // stage 3 (lib/nets.py:101-102)
-  return run_basenet(nets_[4], in3_.all(N), f3_.all(N), N, s);
+  return run_basenet(nets_[4], in3_.all(N), f3_.all(N), N, s, two ? s_hi_ : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -149,7 +149,7 @@ class Engine {
   // the high-band BaseNets of stages 1-2 run on their own stream next to the low-band chain (independent until
   // stage 3, lib/nets.py:88-99); disabled while per-kernel profiling is on so event timings stay per-kernel
   cudaStream_t s_hi_ = nullptr;
-  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_lstm_fork_ = nullptr, ev_lstm_join_ = nullptr;
 
   float2* twiddle_ = nullptr;
   float* window_ = nullptr;
@@ -171,7 +171,8 @@ class Engine {
                      int n, int H, int W, int nin_lstm, int nout_lstm);
   bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s);
   bool run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s);
-  bool run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s);
+  bool run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s,
+                   cudaStream_t side = nullptr);
   bool forward(int N, cudaStream_t s);   // in3_ x-channels already packed for N windows -> f3_
   bool ensure_ws(int64_t T);
   bool ck(cudaError_t e, const char* what);
