@@ -26,6 +26,7 @@ def install():
             raise RuntimeError('librosa.load is outside the hot path and not shimmed')
         m.load = _load
         m.effects = types.SimpleNamespace(trim=None)
+        m._vr_shim = True
         sys.modules['librosa'] = m
     if 'soundfile' not in sys.modules:
         sf = types.ModuleType('soundfile')
@@ -33,6 +34,7 @@ def install():
         def _write(*a, **k):
             raise RuntimeError('soundfile.write is outside the hot path and not shimmed')
         sf.write = _write
+        sf._vr_shim = True
         sys.modules['soundfile'] = sf
 
 
@@ -51,4 +53,8 @@ def import_reference():
     for k in [k for k in sys.modules if k == 'lib' or k.startswith('lib.') or k == 'inference']:
         sys.modules['_ref_' + k] = sys.modules.pop(k)
     sys.path.remove(REFERENCE_ROOT)
+    # the reference modules keep their own references to the stubs; do not leave them importable by anyone else
+    for name in ('librosa', 'soundfile'):
+        if getattr(sys.modules.get(name), '_vr_shim', False):
+            del sys.modules[name]
     return mods

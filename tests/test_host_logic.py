@@ -137,3 +137,40 @@ def test_shard_plan_tiles_the_track():
                     assert f1 < b                                  # ... and the halo frame of its last output hop
                 if count > 0:
                     assert a == max(0, first * roi_ - 64)           # exactly what its windows read (inference.py:44-50)
+
+
+def test_cli_keeps_the_reference_flags():
+    """The 12 flags of the reference CLI (inference.py:109-120), long and short forms."""
+    import subprocess
+    import sys
+    from conftest import PKG
+    out = subprocess.run([sys.executable, os.path.join(PKG, 'inference.py'), '--help'], capture_output=True, text=True,
+                         cwd=PKG).stdout
+    for flag in ('--gpu', '-g', '--pretrained_model', '-P', '--input', '-i', '--sr', '-r', '--n_fft', '-f',
+                 '--hop_length', '-H', '--batchsize', '-B', '--cropsize', '-c', '--output_image', '-I', '--tta', '-t',
+                 '--postprocess', '-p', '--output_dir', '-o'):
+        assert flag in out, flag
+
+
+def test_audio_io_wav_roundtrip(tmp_path):
+    from lib import audio_io
+    rng = np.random.default_rng(0)
+    x = (rng.uniform(-0.9, 0.9, size=(4410, 2))).astype(np.float32)
+    path = str(tmp_path / 'a.wav')
+    audio_io.write(path, x, 44100)
+    y, sr = audio_io.load(path, 44100, mono=False)
+    assert sr == 44100 and y.shape == (2, 4410)
+    assert np.abs(y.T - x).max() < 1e-4   # 16-bit PCM quantisation
+    with pytest.raises(RuntimeError):
+        audio_io.load(path, 22050)
+
+
+def test_artifact_weights_edge_cases():
+    from lib import spec_utils
+    # no frame above the threshold: the reference crashes on idx[0] (lib/spec_utils.py:65); here the mask is unchanged
+    m = np.full((2, 5, 200), 0.01, np.float32)
+    assert np.array_equal(spec_utils.merge_artifacts(m.copy()), m)
+    # one run covering the whole track: no fade-in at frame 0; the reference still fades out before the last frame
+    # because its run end is the last INDEX, which never equals the frame count (lib/spec_utils.py:66,83)
+    w = spec_utils.artifact_weights(np.full(300, 0.5, np.float32))
+    assert w[0] == 1.0 and w[150] == 1.0 and w[-1] == 0.0
