@@ -147,8 +147,15 @@ VR_API int vr_profile_read(vr_ctx* ctx, double* out6);
 VR_API int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w,
                   const float* bias, int32_t Cout, int32_t k, int32_t stride, int32_t dil_h, int32_t dil_w,
                   int32_t act, int32_t use_tc, float* y, void* stream);
+/* One Decoder-shaped layer (lib/layers.py:51-64, BN folded by the caller): low [N][Cl][h][w] is bilinearly
+ * upsampled x2 (align_corners=True), concatenated with skip [N][Cs][2h][2w] and convolved 3x3 -> y [N][Cout][2h][2w];
+ * fused = 1 runs the upsample inside the row-streaming tensor-core kernel, 0 as a separate kernel.              */
+VR_API int vr_debug_decoder(vr_ctx* ctx, const float* low, int32_t N, int32_t Cl, int32_t h, int32_t w, const float* skip,
+                     int32_t Cs, const float* wgt, const float* bias, int32_t Cout, int32_t act, int32_t fused, float* y,
+                     void* stream);
 /* Process-wide debug knobs of the tensor-core kernels: key 0 = 1 sets the UMMA matrix-base-offset field in the
- * row-streaming kernel's shifted descriptors (wrong on B200, kept for tests/diag_rows.py), key 1 = 1 disables that kernel, key 2 = 64 makes it use 64-channel (SW128) chunks instead of 32 (set before vr_create), key 3 = 1 enables the experimental flat-halo kernel (before vr_create).                  */
+ * row-streaming kernel's shifted descriptors (wrong on B200, kept for tests/diag_rows.py), key 1 = 1 disables that kernel, key 2 = 64 makes it use 64-channel (SW128) chunks instead of 32 (set before vr_create), key 3 = 1 enables the experimental flat-halo kernel (before vr_create), key 5 = 1 fuses the decoder upsample into
+ * the row-streaming kernel (before vr_create).                  */
 VR_API int vr_debug_set(int32_t key, int32_t value);
 /* Internal activation of the last forward as NCHW float32; dims receives [N,C,H,W].                       */
 VR_API int vr_debug_read(vr_ctx* ctx, const char* what, float* out, int64_t capacity, int64_t* dims, void* stream);

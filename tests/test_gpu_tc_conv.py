@@ -50,3 +50,42 @@ def test_conv_tcgen05_vs_torch(case):
     # and the CUDA-core kernel agrees with it even more closely (same split-bf16 storage)
     y2 = _run_debug_conv(ctx, x, w, b, k, stride, dil, act, 0)
     assert (y - y2).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+DEC_CASES = [
+    # N, Cl (low-res channels), h, w, Cs (skip channels), Cout, act
+    (1, 64, 4, 64, 32, 32, 1),        # dec1/dec2 class, W = 128
+    (2, 32, 8, 128, 16, 16, 1),       # W = 256: two 128-pixel tiles per row, BN = 16
+    (1, 128, 8, 64, 64, 64, 1),       # four up chunks, two N tiles
+    (1, 80, 4, 64, 32, 32, 2),        # low-res channel count padded to a chunk (96)
+]
+
+
+@pytest.mark.parametrize('case', DEC_CASES)
+def test_decoder_fused_upsample_vs_staged_and_torch(case):
+    """Decoder (lib/layers.py:51-64): bilinear x2 upsample fused into the row-streaming kernel's operand producer."""
+    import torch.nn.functional as F
+    from lib import _native
+    N, Cl, h, w, Cs, Cout, act = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % (2 ** 31))
+    low = torch.randn(N, Cl, h, w, generator=g)
+    skip = torch.randn(N, Cs, 2 * h, 2 * w, generator=g)
+    wgt = torch.randn(Cout, Cl + Cs, 3, 3, generator=g) / ((Cl + Cs) * 9) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ctx = _native.Context(0, 2048, 1024, 32, 128, 256, 1, 0)
+    outs = []
+    for fused in (0, 1):
+        y = torch.empty((N, Cout, 2 * h, 2 * w), dtype=torch.float32, device='cuda')
+        dl, ds, dw, db = low.cuda(), skip.cuda(), wgt.cuda(), b.cuda()
+        ctx.check(ctx.lib.vr_debug_decoder(ctx.handle, _native.ptr(dl), N, Cl, h, w, _native.ptr(ds), Cs,
+                                           _native.ptr(dw), _native.ptr(db), Cout, act, fused, _native.ptr(y),
+                                           _native.stream_ptr()), 'vr_debug_decoder')
+        outs.append(y.cpu())
+    x = torch.cat([F.interpolate(low.double(), scale_factor=2, mode='bilinear', align_corners=True), skip.double()], 1)
+    ref = F.conv2d(x, wgt.double(), b.double(), padding=1)
+    ref = F.relu(ref) if act == 1 else F.leaky_relu(ref, 0.01)
+    tol = 2e-4 * max(1.0, ref.abs().max().item())
+    assert (outs[0] - ref.float()).abs().max().item() < tol
+    assert (outs[1] - ref.float()).abs().max().item() < tol
+    # same interpolation arithmetic, same products: the two paths agree to accumulation-order noise
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

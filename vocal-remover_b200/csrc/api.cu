@@ -252,6 +252,14 @@ int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H
                                         (cudaStream_t)stream));
 }
 
+int vr_debug_decoder(vr_ctx* ctx, const float* low, int32_t N, int32_t Cl, int32_t h, int32_t w, const float* skip,
+                     int32_t Cs, const float* wgt, const float* bias, int32_t Cout, int32_t act, int32_t fused, float* y,
+                     void* stream) {
+  CHECK_CTX(ctx);
+  return done(ctx, ctx->eng->debug_decoder(low, N, Cl, h, w, skip, Cs, wgt, bias, Cout, act, fused, y,
+                                           (cudaStream_t)stream));
+}
+
 int vr_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 8) return -1;
   vr::g_tc_debug[key] = value;

@@ -317,6 +317,14 @@ bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out) {
   return tc_encode_fn() != nullptr;
 }
 
+bool tc_can_fuse_upsample(const ConvLayer& L, const ActView& in, const ActView& out, const ActView& up_src) {
+  if (!L.tc || g_tc_debug[5] != 1) return false;
+  const TcConv& tc = *L.tc;
+  if (!tc_rows_supported(L, tc, in, out) || tc.rows.KB != 32) return false;
+  return up_src.C % 32 == 0 && up_src.C <= tc.rows.CinPadR && up_src.H * 2 == in.H && up_src.W * 2 == in.W &&
+         up_src.sw % 8 == 0;
+}
+
 bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
   if (!(L.k == 1 || L.k == 3) || L.Cout < 4) return true;   // stays on the CUDA-core kernel
   auto tc = std::make_shared<TcConv>();
@@ -377,9 +385,14 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
   return true;
 }
 
-cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err) {
+cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err,
+                      const ActView* up_src) {
   TcConv& tc = *L.tc;
-  if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err);
+  if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err, up_src);
+  if (up_src) {
+    err = "tc_launch: fused upsample is only implemented in the row-streaming kernel";
+    return cudaErrorInvalidValue;
+  }
   if (tc_flat_supported(L, tc, in, out)) return tc_flat_launch(L, tc, in, out, s, err);
   const TileGeom g = tile_geom(out.H, out.W);
   auto key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);

@@ -18,6 +18,12 @@
 //     N = 16/32 the single issuing thread, not the tensor pipe, was the limit);
 //   * the 9-tap weight slab of the chunk (3 kw x [3*BN] x 64, hi+lo) is double-buffered in shared memory.
 // L2->SM traffic per output pixel drops from 9 to (R+2)/R = 1.25 operand fetches.
+//
+// Fused decoder upsample (optional, Decoder of lib/layers.py:51-64): the leading `up_chunks` channel chunks of the
+// input are F.interpolate(x2, bilinear, align_corners=True) of a tensor at half resolution.  Instead of reading a
+// materialised up-sampled copy (4x the bytes, and the decoder layers are HBM-bound), eight producer warps
+// interpolate each 130-pixel row straight from the low-resolution tensor into the swizzled operand slot
+// (generic-proxy stores + fence.proxy.async + mbarrier arrive), bit-identical to upsample2x_kernel.
 #include <stdio.h>
 
 #include "engine.h"
@@ -26,7 +32,8 @@
 
 namespace vr {
 
-static constexpr int kRowsThreads = 192;
+static constexpr int kRowsThreads = 192 + 256;      // TMA, MMA, 4 epilogue warps + 8 interpolation warps
+static constexpr int kInterpThreads = 256;
 static constexpr int kMaxR = 8;                    // output rows per CTA tile (runtime: 8, or 4 with two CTAs per SM)
 static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
 static constexpr int kMaxASlots = 8;
@@ -44,9 +51,19 @@ struct RowsParams {
   const float* bias;
   int tmem_cols;
   int bo_mode;
+  // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
+  int up_chunks, xH, xW, xC;
+  int n_uslots;   // A slots [0, n_uslots) form the ring of the interpolation warps, [n_uslots, n_aslots) the TMA ring:
+                  // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
+                  // parity cannot tell 'two uses behind' from 'up to date')
+  const bf16* x_hi;
+  const bf16* x_lo;
+  int64_t xsn, xsh;
+  int xsw;
+  float up_sh, up_sw;
 };
 
-__global__ void __launch_bounds__(kRowsThreads, 2)
+__global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
     {
-      int as = 0, bs = 0;
+      int as = p.n_uslots, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
@@ -121,6 +138,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
             bph ^= 1u;
           }
           for (int r = 0; r < p.R + 2; ++r) {
+            if (cc < p.up_chunks) continue;   // rows of this chunk are produced by the interpolation warps
             mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
             const uint32_t afull = smem_u32(&bar_afull[as]);
             const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
@@ -131,7 +149,7 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
             }
             __syncwarp();
             if (++as == p.n_aslots) {
-              as = 0;
+              as = p.n_uslots;
               aph ^= 1u;
             }
           }
@@ -141,8 +159,8 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
     {
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      int as_t = p.n_uslots, as_u = 0, bs = 0, acc = 0;
+      uint32_t aph_t = 0, aph_u = 0, bph = 0, acc_phase = 0;
       const uint32_t row_bytes = (uint32_t)(p.KB * 2);
       const uint32_t b3_plane = (uint32_t)(3 * p.BN) * row_bytes;   // hi -> lo plane inside one kw slab
       const uint32_t dhi = desc_hi((uint32_t)p.sbo, (uint32_t)p.layout);
@@ -153,8 +171,10 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
         for (int cc = 0; cc < p.chunks; ++cc) {
           mbar_wait(smem_u32(&bar_bfull[bs]), bph);
           const uint32_t bsrc = b_base + (uint32_t)(bs * p.b_buf_bytes);
+          const bool up = cc < p.up_chunks;
           for (int r = 0; r < p.R + 2; ++r) {
-            mbar_wait(smem_u32(&bar_afull[as]), aph);
+            const int as = up ? as_u : as_t;
+            mbar_wait(smem_u32(&bar_afull[as]), up ? aph_u : aph_t);
             tc_fence_after();
             const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * p.a_slot));
             const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * p.a_slot + p.a_plane));
@@ -201,9 +221,16 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
               umma_commit(smem_u32(&bar_aempty[as]));
             }
             __syncwarp();
-            if (++as == p.n_aslots) {
-              as = 0;
-              aph ^= 1u;
+            if (up) {
+              if (++as_u == p.n_uslots) {
+                as_u = 0;
+                aph_u ^= 1u;
+              }
+            } else {
+              if (++as_t == p.n_aslots) {
+                as_t = p.n_uslots;
+                aph_t ^= 1u;
+              }
             }
           }
           if (elect_one_sync()) umma_commit(smem_u32(&bar_bempty[bs]));
@@ -216,6 +243,74 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== bilinear x2 producer (8 warps) =====================
+    if (p.up_chunks > 0) {
+      const int tid = threadIdx.x - 192;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * 128;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.R;
+        const int n = mt / p.tiles_h;
+        for (int cc = 0; cc < p.up_chunks; ++cc) {
+          for (int r = 0; r < p.R + 2; ++r) {
+            {
+              mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
+              uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * p.a_slot;
+              const int h = h0 - 1 + r;
+              const bool row_ok = h >= 0 && h < p.H;
+              // ATen upsample_bilinear2d, align_corners=True (same arithmetic as upsample2x_kernel)
+              const float fy = p.up_sh * (row_ok ? h : 0);
+              const int y0 = (int)fy;
+              const int y1 = y0 + (y0 < p.xH - 1 ? 1 : 0);
+              const float ly = fy - y0, hy = 1.f - ly;
+              const int64_t rb0 = (int64_t)n * p.xsn + (int64_t)y0 * p.xsh + cc * 32;
+              const int64_t rb1 = (int64_t)n * p.xsn + (int64_t)y1 * p.xsh + cc * 32;
+              for (int item = tid; item < kRowPx * 4; item += kInterpThreads) {
+                const int q = item >> 2, j = item & 3;          // pixel of the slot, 8-channel group
+                const int w = w0 - 1 + q;
+                bf16x8 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
+                if (row_ok && w >= 0 && w < p.W && cc * 32 + j * 8 < p.xC) {
+                  const float fx = p.up_sw * w;
+                  const int x0 = (int)fx;
+                  const int x1 = x0 + (x0 < p.xW - 1 ? 1 : 0);
+                  const float lx = fx - x0, hx = 1.f - lx;
+                  const int64_t o00 = rb0 + (int64_t)x0 * p.xsw + j * 8, o01 = rb0 + (int64_t)x1 * p.xsw + j * 8;
+                  const int64_t o10 = rb1 + (int64_t)x0 * p.xsw + j * 8, o11 = rb1 + (int64_t)x1 * p.xsw + j * 8;
+                  const bf16x8 ah = ld128(p.x_hi + o00), al = ld128(p.x_lo + o00);
+                  const bf16x8 bh = ld128(p.x_hi + o01), bl = ld128(p.x_lo + o01);
+                  const bf16x8 ch = ld128(p.x_hi + o10), cl = ld128(p.x_lo + o10);
+                  const bf16x8 dh = ld128(p.x_hi + o11), dl = ld128(p.x_lo + o11);
+                  float a[8], b[8], c[8], d[8], y[8];
+                  unpack8(ah, al, a);
+                  unpack8(bh, bl, b);
+                  unpack8(ch, cl, c);
+                  unpack8(dh, dl, d);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+                  split8(y, oh, ol);
+                }
+                // SWIZZLE_64B (same pattern TMA writes and UMMA reads): 16-byte chunk j of 64-byte row q sits at
+                // chunk j ^ ((q >> 1) & 3) because the XOR takes address bits [7,9) and the slot is 1 KiB aligned
+                const int off = q * 64 + ((j ^ ((q >> 1) & 3)) << 4);
+                *reinterpret_cast<uint4*>(slot + off) = oh;
+                *reinterpret_cast<uint4*>(slot + p.a_plane + off) = ol;
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (tid == 0) mbar_arrive(smem_u32(&bar_afull[as]));
+            }
+            if (++as == p.n_uslots) {
+              as = 0;
+              aph ^= 1u;
+            }
+          }
         }
       }
     }
@@ -344,9 +439,16 @@ bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, 
   return true;
 }
 
+// up_src != nullptr: the first up_src->C channels of `in` are NOT read; they are produced inside the kernel as the
+// bilinear x2 upsample of *up_src (half resolution).  Needs 32-channel chunks and up_src->C % 32 == 0.
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
-                           std::string& err) {
+                           std::string& err, const ActView* up_src) {
   TcRowsPlan& R = tc.rows;
+  if (up_src && (R.KB != 32 || up_src->C % 32 || up_src->H * 2 != in.H || up_src->W * 2 != in.W ||
+                 up_src->sw % 8 || up_src->C > R.CinPadR)) {
+    err = "tc_rows_launch: fused upsample needs 32-channel chunks and a half-resolution source of 32k channels";
+    return cudaErrorInvalidValue;
+  }
   ViewKey key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
   auto it = R.map_a.find(key);
   if (it == R.map_a.end()) {
@@ -374,7 +476,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.N = out.N; p.H = out.H; p.W = out.W;
   // g_tc_debug[4] = 1: two CTAs per SM (4 rows per tile, 32-channel chunks, 2 row slots, <= 256 TMEM columns each)
   // so that two MMA-issuing threads feed the tensor pipe; needs the 32-channel chunk layout
-  const bool dual = g_tc_debug[4] == 1 && R.KB == 32;
+  const bool dual = false;   // two CTAs per SM measured neutral and no longer fits next to the interpolation warps
   p.R = dual ? 4 : kMaxR;
   p.tiles_w = out.W / 128; p.tiles_h = out.H / p.R; p.n_tiles = R.n_tiles;
   p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
@@ -392,6 +494,16 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.bias = R.bias;
   p.tmem_cols = 2 * p.R * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
   p.bo_mode = g_tc_debug[0];
+  p.up_chunks = 0; p.xH = p.xW = p.xC = 0; p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
+  p.up_sh = p.up_sw = 0.f;
+  if (up_src) {
+    p.up_chunks = up_src->C / 32;
+    p.xH = up_src->H; p.xW = up_src->W; p.xC = up_src->C;
+    p.x_hi = up_src->hi; p.x_lo = up_src->lo;
+    p.xsn = up_src->sn; p.xsh = up_src->sh; p.xsw = up_src->sw;
+    p.up_sh = in.H > 1 ? (float)(up_src->H - 1) / (float)(in.H - 1) : 0.f;   // as launch_upsample2x
+    p.up_sw = in.W > 1 ? (float)(up_src->W - 1) / (float)(in.W - 1) : 0.f;
+  }
   static bool attr_set = false;
   static int num_sms = 0, max_smem = 0;
   if (!attr_set) {
@@ -410,6 +522,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     err = "tc_rows_launch: shared memory too small";
     return cudaErrorInvalidValue;
   }
+  p.n_uslots = p.up_chunks > 0 ? p.n_aslots / 2 : 0;
   const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + 1024;
   const int ctas = dual ? 2 * num_sms : num_sms;
   const int grid = p.total_tiles < ctas ? p.total_tiles : ctas;

@@ -197,9 +197,11 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     err = "unsupported geometry: band height and cropsize must be multiples of 16 and nout a multiple of 16";
     return false;
   }
-  // lstm channel + 15 zero channels keep every slice 32-byte aligned (full-sector 256-bit epilogue stores)
-  const int c1 = round_up(3 * n + 16, 16);
-  P.e1_off = 2 * n + 16;
+  // lstm channel + 15 zero channels keep every slice 32-byte aligned (full-sector 256-bit epilogue stores); with the
+  // fused decoder upsample the group is a whole 32-channel chunk so that chunks are either upsampled or skip data
+  const int lg = (g_tc_debug[5] == 1 && (2 * n) % 32 == 0) ? 32 : 16;
+  const int c1 = round_up(3 * n + lg, 16);
+  P.e1_off = 2 * n + lg;
   P.cat1 = make_buffer(Nb, H, W, c1);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
@@ -219,7 +221,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.ao = make_buffer(Nb, H / 16, W / 16, 8 * n);
   P.d4 = make_buffer(Nb, H / 8, W / 8, 6 * n);
   P.d3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
-  P.d2 = make_buffer(Nb, H / 2, W / 2, 2 * n + 16);
+  P.d2 = make_buffer(Nb, H / 2, W / 2, 2 * n + lg);
   if (!P.d2.hi || !P.cat1.hi) return false;
 
   if (!make_conv(P.enc1, prefix + ".enc1", in_perm, cin_pad, 3, 1, 1, 1, ACT_RELU)) return false;
@@ -250,7 +252,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     return false;
   {
     // dec1 input in the reference: cat[ up(cat[h (2n), lstm (1)]) , e1 (n) ]  (lib/nets.py:38-39, layers.py:52-56)
-    // packed as [ up(h) 2n | up(lstm) 1 | 15 zeros | e1 n | zeros ]
+    // packed as [ up(h) 2n | up(lstm) 1 | 15 or 31 zeros | e1 n | zeros ]
     std::vector<int> perm((size_t)c1, -1);
     for (int i = 0; i < 2 * n + 1; ++i) perm[(size_t)i] = i;
     for (int i = 0; i < n; ++i) perm[(size_t)(P.e1_off + i)] = 2 * n + 1 + i;
@@ -433,7 +435,7 @@ bool Engine::profile_read(double* out6) {
   return true;
 }
 
-bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s) {
+bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src) {
   ++launches;
   const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
   ProfRec rec;
@@ -445,7 +447,7 @@ bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaS
     rec.flops = 2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k;
     cudaEventRecord(rec.a, s);
   }
-  bool ok = run_conv_inner(L, in, out, use_tc, s);
+  bool ok = run_conv_inner(L, in, out, use_tc, s, up_src);
   if (profiling_) {
     cudaEventRecord(rec.b, s);
     prof_.push_back(rec);
@@ -453,8 +455,13 @@ bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   return ok;
 }
 
-bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s) {
-  if (use_tc) return ck(tc_launch(L, in, out, s, err), L.name.c_str());
+bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s,
+                            const ActView* up_src) {
+  if (use_tc) return ck(tc_launch(L, in, out, s, err, up_src), L.name.c_str());
+  if (up_src) {
+    err = "internal: fused upsample requested for a CUDA-core convolution";
+    return false;
+  }
   ConvParams p;
   p.in = in; p.out = out;
   p.w = L.w; p.bias = L.bias;
@@ -465,6 +472,16 @@ bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out,
   p.act = L.act;
   p.in.C = L.CinPad;
   return ck(launch_conv_simt(p, s), L.name.c_str());
+}
+
+bool Engine::run_decoder(ConvLayer& L, const ActView& low, const Buffer& cat, int N, const ActView& out,
+                         cudaStream_t s) {
+  const ActView cat_all = cat.all(N);
+  if (cfg_.conv_mode == 0 && L.tc && tc_supported(L, cat_all, out) && tc_can_fuse_upsample(L, cat_all, out, low))
+    return run_conv(L, cat_all, out, s, &low);   // channels [0, low.C) of cat are produced inside the kernel
+  ++launches;
+  if (!ck(launch_upsample2x(low, cat.view(N, 0, cat.H, 0, low.C), s), "decoder upsample")) return false;
+  return run_conv(L, cat_all, out, s);
 }
 
 bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s,
@@ -491,13 +508,12 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
     if (!run_conv(P.aspp_d[i], P.e5.all(N), P.acat.view(N, 0, h16, (2 + i) * c8, c8), s)) return false;
   if (!run_conv(P.bott, P.acat.all(N), P.ao.all(N), s)) return false;
   // decoders (lib/nets.py:35-37, lib/layers.py:51-64)
-  launches += 3;
+  launches += 2;
   if (!ck(launch_upsample2x(P.ao.all(N), P.cat4.view(N, 0, H / 8, 0, 8 * n), s), "up4")) return false;
   if (!run_conv(P.dec[0], P.cat4.all(N), P.d4.all(N), s)) return false;
   if (!ck(launch_upsample2x(P.d4.all(N), P.cat3.view(N, 0, H / 4, 0, 6 * n), s), "up3")) return false;
   if (!run_conv(P.dec[1], P.cat3.all(N), P.d3.all(N), s)) return false;
-  if (!ck(launch_upsample2x(P.d3.all(N), P.cat2.view(N, 0, H / 2, 0, 4 * n), s), "up2")) return false;
-  if (!run_conv(P.dec[2], P.cat2.all(N), P.d2.view(N, 0, H / 2, 0, 2 * n), s)) return false;
+  if (!run_decoder(P.dec[2], P.d3.all(N), P.cat2, N, P.d2.view(N, 0, H / 2, 0, 2 * n), s)) return false;
   // LSTM branch -> channel 2n of d2 (lib/nets.py:38, lib/layers.py:124-133).  Its 128-step recurrence keeps only
   // 2N CTAs busy, so when a side stream is free (stage 3) it runs there while the main stream upsamples the 2n
   // convolution channels of d2; only the LSTM channel's 16-channel group is upsampled after the join.
@@ -518,17 +534,23 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
           "lstm dense"))
     return false;
   // dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
+  const int upc = P.e1_off;   // channels of d2 that are upsampled: 2n conv channels + the LSTM channel group
   if (overlap) {
-    ++launches;
     if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join")) return false;
+    if (cfg_.conv_mode == 0 && tc_can_fuse_upsample(P.dec[3], P.cat1.all(N), out, P.d2.all(N))) {
+      // fused: the convolution reads d2 (incl. the LSTM channel) itself, so it simply waits for the side stream
+      if (!ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join")) return false;
+      return run_decoder(P.dec[3], P.d2.all(N), P.cat1, N, out, s);
+    }
+    ++launches;
     if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 0, 2 * n), P.cat1.view(N, 0, H, 0, 2 * n), s), "up1")) return false;
     if (!ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join")) return false;
-    if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 2 * n, 16), P.cat1.view(N, 0, H, 2 * n, 16), s), "up1 lstm"))
+    if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 2 * n, upc - 2 * n), P.cat1.view(N, 0, H, 2 * n, upc - 2 * n), s),
+            "up1 lstm"))
       return false;
-  } else {
-    if (!ck(launch_upsample2x(P.d2.all(N), P.cat1.view(N, 0, H, 0, 2 * n + 16), s), "up1")) return false;
+    return run_conv(P.dec[3], P.cat1.all(N), out, s);
   }
-  return run_conv(P.dec[3], P.cat1.all(N), out, s);
+  return run_decoder(P.dec[3], P.d2.all(N), P.cat1, N, out, s);
 }
 
 bool Engine::forward(int N, cudaStream_t s) {
@@ -828,6 +850,66 @@ bool Engine::debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const
   cfg_.conv_mode = saved_mode;
   if (ok) ok = ck(launch_act_to_nchw(bout.view(N, 0, Ho, 0, Cout), Cout, y_nchw, s), "act_to_nchw");
   if (ok) ok = ck(cudaStreamSynchronize(s), "debug_conv sync");
+  L.tc.reset();
+  for (void* p : allocs_) cudaFree(p);
+  allocs_.clear();
+  std::swap(tmp, allocs_);
+  return ok;
+}
+
+// Test hook for the decoder path: y = act(conv3x3(cat[up2x(low), skip]) + bias), fused (upsample inside the row
+// kernel) or staged (upsample kernel, then convolution).
+bool Engine::debug_decoder(const float* low_nchw, int N, int Cl, int h, int w, const float* skip_nchw, int Cs,
+                           const float* wgt, const float* bias, int Cout, int act, int fused, float* y_nchw,
+                           cudaStream_t s) {
+  cudaSetDevice(cfg_.device);
+  const int H = 2 * h, W = 2 * w, Cin = Cl + Cs;
+  const int cl_pad = round_up(Cl, 32), cin_pad = round_up(cl_pad + Cs, 16);
+  std::vector<void*> tmp;
+  std::swap(tmp, allocs_);
+  Buffer blow = make_buffer(N, h, w, cl_pad);
+  Buffer bcat = make_buffer(N, H, W, cin_pad);
+  Buffer bout = make_buffer(N, H, W, round_up(Cout, 16));
+  ConvLayer L;
+  L.name = "debug_decoder";
+  L.Cin = Cin; L.CinPad = cin_pad; L.Cout = Cout; L.CoutPad = round_up(Cout, 8);
+  L.k = 3; L.stride = 1; L.dil_h = 1; L.dil_w = 1; L.act = act;
+  std::vector<float> hw((size_t)Cout * Cin * 9), hb((size_t)Cout);
+  cudaMemcpyAsync(hw.data(), wgt, hw.size() * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(hb.data(), bias, hb.size() * sizeof(float), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  L.w_host.assign((size_t)9 * L.CinPad * L.CoutPad, 0.f);
+  L.bias_host.assign((size_t)L.CoutPad, 0.f);
+  for (int co = 0; co < Cout; ++co) {
+    L.bias_host[(size_t)co] = hb[(size_t)co];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const int pc = ci < Cl ? ci : cl_pad + (ci - Cl);   // packed position: [up Cl | pad | skip Cs]
+      for (int t = 0; t < 9; ++t)
+        L.w_host[((size_t)t * L.CinPad + pc) * L.CoutPad + co] = hw[((size_t)co * Cin + ci) * 9 + t];
+    }
+  }
+  L.w = (float*)dalloc(L.w_host.size() * sizeof(float));
+  L.bias = (float*)dalloc(L.bias_host.size() * sizeof(float));
+  bool ok = blow.hi && bcat.hi && bout.hi && L.w && L.bias;
+  if (ok) {
+    cudaMemcpy(L.w, L.w_host.data(), L.w_host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(L.bias, L.bias_host.data(), L.bias_host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    ok = ck(launch_nchw_to_act(low_nchw, Cl, blow.all(N), s), "nchw_to_act low") &&
+         ck(launch_nchw_to_act(skip_nchw, Cs, bcat.view(N, 0, H, cl_pad, cin_pad - cl_pad), s), "nchw_to_act skip");
+  }
+  if (ok) ok = tc_prepare(L, err, allocs_);
+  const int saved_mode = cfg_.conv_mode, saved_fuse = g_tc_debug[5];
+  cfg_.conv_mode = 0;
+  g_tc_debug[5] = fused ? 1 : 0;
+  if (ok && fused && !tc_can_fuse_upsample(L, bcat.all(N), bout.view(N, 0, H, 0, Cout), blow.all(N))) {
+    err = "debug_decoder: geometry not supported by the fused row kernel";
+    ok = false;
+  }
+  if (ok) ok = run_decoder(L, blow.all(N), bcat, N, bout.view(N, 0, H, 0, Cout), s);
+  cfg_.conv_mode = saved_mode;
+  g_tc_debug[5] = saved_fuse;
+  if (ok) ok = ck(launch_act_to_nchw(bout.view(N, 0, H, 0, Cout), Cout, y_nchw, s), "act_to_nchw");
+  if (ok) ok = ck(cudaStreamSynchronize(s), "debug_decoder sync");
   L.tc.reset();
   for (void* p : allocs_) cudaFree(p);
   allocs_.clear();

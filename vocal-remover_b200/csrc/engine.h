@@ -114,6 +114,8 @@ class Engine {
   // debug / tests: run one reference Conv2DBNActiv-shaped layer through a chosen kernel
   bool debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const float* w, const float* bias, int Cout,
                   int k, int stride, int dil_h, int dil_w, int act, int use_tc, float* y_nchw, cudaStream_t s);
+  bool debug_decoder(const float* low_nchw, int N, int Cl, int h, int w, const float* skip_nchw, int Cs, const float* wgt,
+                     const float* bias, int Cout, int act, int fused, float* y_nchw, cudaStream_t s);
   // debug: copy an internal activation (by name) of the last forward to NCHW fp32
   bool debug_read(const char* what, float* out, int64_t cap, int64_t* dims, cudaStream_t s);
 
@@ -169,8 +171,12 @@ class Engine {
                  int dh, int dw, int act);
   bool build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, const std::vector<int>& in_perm, int cin_pad,
                      int n, int H, int W, int nin_lstm, int nout_lstm);
-  bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s);
-  bool run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s);
+  bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src = nullptr);
+  bool run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s,
+                      const ActView* up_src);
+  // Decoder (lib/layers.py:51-64): upsample `low` into channels [0, low.C) of `cat`, then conv(cat) -> out; the
+  // upsample is fused into the convolution's operand producer when the row kernel can do it
+  bool run_decoder(ConvLayer& L, const ActView& low, const Buffer& cat, int N, const ActView& out, cudaStream_t s);
   bool run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, int N, cudaStream_t s,
                    cudaStream_t side = nullptr);
   bool forward(int N, cudaStream_t s);   // in3_ x-channels already packed for N windows -> f3_
@@ -181,6 +187,8 @@ class Engine {
 // conv_tc.cu
 bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out);
 bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs);
-cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err);
+cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err,
+                      const ActView* up_src = nullptr);
+bool tc_can_fuse_upsample(const ConvLayer& L, const ActView& in, const ActView& out, const ActView& up_src);
 
 }  // namespace vr

@@ -47,12 +47,12 @@ float tc_bf2f(uint16_t h);
 bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<void*>& allocs);
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
-                           std::string& err);
+                           std::string& err, const ActView* up_src = nullptr);
 // conv_tc_flat.cu
 bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err);
 bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_flat_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err);
-extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable it, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = 1: rows kernel with two CTAs per SM
+extern int g_tc_debug[8];   // [0] base-offset mode of the rows kernel, [1] disable it, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] unused, [5] = 1: decoder upsample fused into the row kernel
 
 }  // namespace vr

@@ -50,6 +50,8 @@ SIGNATURES = {
     'vr_profile_read': (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
     'vr_debug_conv': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_i32, c_i32, c_fp, c_vp]),
+    'vr_debug_decoder': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32,
+                                 c_fp, c_vp]),
     'vr_debug_set': (c_i32, [c_i32, c_i32]),
     'vr_debug_read': (c_i32, [c_vp, ctypes.c_char_p, c_fp, c_i64, ctypes.POINTER(c_i64), c_vp]),
 }
@@ -76,8 +78,8 @@ def load_library():
         lib.vr_debug_set(2, int(os.environ['VR_ROWS_KB']))
     if os.environ.get('VR_FLAT'):
         lib.vr_debug_set(3, int(os.environ['VR_FLAT']))
-    if os.environ.get('VR_ROWS_DUAL'):
-        lib.vr_debug_set(4, int(os.environ['VR_ROWS_DUAL']))
+    if os.environ.get('VR_FUSE_UP'):
+        lib.vr_debug_set(5, int(os.environ['VR_FUSE_UP']))
     if os.environ.get('VR_NO_ROWS'):
         lib.vr_debug_set(1, int(os.environ['VR_NO_ROWS']))
     _lib = lib
