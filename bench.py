@@ -302,7 +302,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200')
-    ap.add_argument('--batch', type=int, default=32, help='windows per forward launch sequence')
+    ap.add_argument('--batch', type=int, default=27, help='windows per forward launch sequence (240 s = 81 windows = 3 x 27)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU arm (profiling runs only)')
     ap.add_argument('--seconds-per-gpu', type=float, default=SECONDS_PER_GPU,
                     help='track length per GPU (default 240 s = BASELINE configs[2]; shorter only for profiling)')

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // host side
-int g_tc_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_tc_debug[8] = {0, 0, 0, 0, 0, 1, 0, 0};   // [5] = 1: fused decoder upsample on by default
 
 EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;

@@ -32,11 +32,14 @@
 
 namespace vr {
 
-static constexpr int kRowsThreads = 192 + 256;      // TMA, MMA, 4 epilogue warps + 8 interpolation warps
-static constexpr int kInterpThreads = 256;
+static constexpr int kInterpThreads = 288;          // 9 warps: 520 slot items in two passes, 272 source items in one
+static constexpr int kRowsThreads = 192 + kInterpThreads;   // TMA, MMA, 4 epilogue warps + the interpolation warps
 static constexpr int kMaxR = 8;                    // output rows per CTA tile (runtime: 8, or 4 with two CTAs per SM)
 static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
 static constexpr int kMaxASlots = 8;
+static constexpr int kSrcPx = 68;                  // half-resolution pixels staged per source row (fused upsample)
+static constexpr int kStageBytes = 4 * kSrcPx * 64;   // {hi,lo} x {y0,y1} x kSrcPx x 32 channels
+static constexpr int kStages = 2;
 
 struct RowsParams {
   int N, H, W, R, tiles_w, tiles_h, n_tiles, total_tiles;
@@ -65,7 +68,7 @@ struct RowsParams {
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                        const RowsParams p) {
+                        const __grid_constant__ CUtensorMap tmX, const RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_afull[kMaxASlots];
   __shared__ __align__(8) uint64_t bar_aempty[kMaxASlots];
@@ -73,6 +76,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   __shared__ __align__(8) uint64_t bar_bempty[2];
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_sfull[kStages];    // half-resolution source rows staged by TMA (fused upsample)
+  __shared__ __align__(8) uint64_t bar_sempty[kStages];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[256];   // folded-BN bias of every N tile, staged once (a global load per use stalled the epilogue)
 
@@ -81,6 +86,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + (uint32_t)(p.n_aslots * p.a_slot);
+  const uint32_t s_base = b_base + (uint32_t)(2 * p.b_buf_bytes);
+  const uint32_t v_base = s_base + (uint32_t)(kStages * kStageBytes);   // fp32 vertically blended source row
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -94,6 +101,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       mbar_init(smem_u32(&bar_bempty[s]), 1);
       mbar_init(smem_u32(&bar_tfull[s]), 1);
       mbar_init(smem_u32(&bar_tempty[s]), 4);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bar_sfull[s]), 1);
+      mbar_init(smem_u32(&bar_sempty[s]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -112,8 +123,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
     {
-      int as = p.n_uslots, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int as = p.n_uslots, bs = 0, ss = 0;
+      uint32_t aph = 0, bph = 0, sph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         int mt = tile / p.n_tiles;
@@ -138,7 +149,36 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             bph ^= 1u;
           }
           for (int r = 0; r < p.R + 2; ++r) {
-            if (cc < p.up_chunks) continue;   // rows of this chunk are produced by the interpolation warps
+            if (cc < p.up_chunks) {
+              // rows of this chunk are produced by the interpolation warps; stage their two half-resolution source
+              // rows (hi and lo planes) in shared memory so that each source pixel crosses L2->SM once per row
+              mbar_wait(smem_u32(&bar_sempty[ss]), sph ^ 1u);
+              const uint32_t sfull = smem_u32(&bar_sfull[ss]);
+              const uint32_t sdst = s_base + (uint32_t)(ss * kStageBytes);
+              const int h = h0 - 1 + r;
+              if (elect_one_sync()) {
+                if (h >= 0 && h < p.H) {
+                  const float fy = p.up_sh * h;
+                  const int y0 = (int)fy;
+                  const int y1 = y0 + (y0 < p.xH - 1 ? 1 : 0);
+                  const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
+                  mbar_expect_tx(sfull, (uint32_t)kStageBytes);
+#pragma unroll
+                  for (int pl = 0; pl < 2; ++pl) {
+                    tma_load_5d(sdst + (uint32_t)((pl * 2 + 0) * kSrcPx * 64), &tmX, cc * 32, xs, y0, n, pl, sfull);
+                    tma_load_5d(sdst + (uint32_t)((pl * 2 + 1) * kSrcPx * 64), &tmX, cc * 32, xs, y1, n, pl, sfull);
+                  }
+                } else {
+                  mbar_arrive(sfull);   // halo row outside the image: the interpolation warps write zeros
+                }
+              }
+              __syncwarp();
+              if (++ss == kStages) {
+                ss = 0;
+                sph ^= 1u;
+              }
+              continue;
+            }
             mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
             const uint32_t afull = smem_u32(&bar_afull[as]);
             const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
@@ -247,68 +287,86 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       }
     }
   } else if (warp >= 6) {
-    // ===================== bilinear x2 producer (8 warps) =====================
+    // ===================== bilinear x2 producer (9 warps) =====================
+    // Per A-slot row: (A) blend the two staged half-resolution source rows vertically into an fp32 row in shared
+    // memory, (B) blend horizontally per output pixel, split to hi/lo and store in the SW64 slot layout.
+    // align_corners=True weights as ATen upsample_bilinear2d / upsample2x_kernel (vertical blend first here).
     if (p.up_chunks > 0) {
       const int tid = threadIdx.x - 192;
-      int as = 0;
-      uint32_t aph = 0;
+      int as = 0, ss = 0;
+      uint32_t aph = 0, sph = 0;
+      float4* v0 = reinterpret_cast<float4*>(smem_raw + (v_base - smem_u32(smem_raw)));   // channels 8j..8j+3
+      float4* v1 = v0 + kSrcPx * 4;                                                       // channels 8j+4..8j+7
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int mt = tile / p.n_tiles;
         const int w0 = (mt % p.tiles_w) * 128;
         mt /= p.tiles_w;
         const int h0 = (mt % p.tiles_h) * p.R;
-        const int n = mt / p.tiles_h;
+        const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
         for (int cc = 0; cc < p.up_chunks; ++cc) {
           for (int r = 0; r < p.R + 2; ++r) {
-            {
-              mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
-              uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * p.a_slot;
-              const int h = h0 - 1 + r;
-              const bool row_ok = h >= 0 && h < p.H;
-              // ATen upsample_bilinear2d, align_corners=True (same arithmetic as upsample2x_kernel)
-              const float fy = p.up_sh * (row_ok ? h : 0);
-              const int y0 = (int)fy;
-              const int y1 = y0 + (y0 < p.xH - 1 ? 1 : 0);
-              const float ly = fy - y0, hy = 1.f - ly;
-              const int64_t rb0 = (int64_t)n * p.xsn + (int64_t)y0 * p.xsh + cc * 32;
-              const int64_t rb1 = (int64_t)n * p.xsn + (int64_t)y1 * p.xsh + cc * 32;
-              for (int item = tid; item < kRowPx * 4; item += kInterpThreads) {
-                const int q = item >> 2, j = item & 3;          // pixel of the slot, 8-channel group
-                const int w = w0 - 1 + q;
-                bf16x8 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
-                if (row_ok && w >= 0 && w < p.W && cc * 32 + j * 8 < p.xC) {
-                  const float fx = p.up_sw * w;
-                  const int x0 = (int)fx;
-                  const int x1 = x0 + (x0 < p.xW - 1 ? 1 : 0);
-                  const float lx = fx - x0, hx = 1.f - lx;
-                  const int64_t o00 = rb0 + (int64_t)x0 * p.xsw + j * 8, o01 = rb0 + (int64_t)x1 * p.xsw + j * 8;
-                  const int64_t o10 = rb1 + (int64_t)x0 * p.xsw + j * 8, o11 = rb1 + (int64_t)x1 * p.xsw + j * 8;
-                  const bf16x8 ah = ld128(p.x_hi + o00), al = ld128(p.x_lo + o00);
-                  const bf16x8 bh = ld128(p.x_hi + o01), bl = ld128(p.x_lo + o01);
-                  const bf16x8 ch = ld128(p.x_hi + o10), cl = ld128(p.x_lo + o10);
-                  const bf16x8 dh = ld128(p.x_hi + o11), dl = ld128(p.x_lo + o11);
-                  float a[8], b[8], c[8], d[8], y[8];
-                  unpack8(ah, al, a);
-                  unpack8(bh, bl, b);
-                  unpack8(ch, cl, c);
-                  unpack8(dh, dl, d);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) y[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
-                  split8(y, oh, ol);
-                }
-                // SWIZZLE_64B (same pattern TMA writes and UMMA reads): 16-byte chunk j of 64-byte row q sits at
-                // chunk j ^ ((q >> 1) & 3) because the XOR takes address bits [7,9) and the slot is 1 KiB aligned
-                const int off = q * 64 + ((j ^ ((q >> 1) & 3)) << 4);
-                *reinterpret_cast<uint4*>(slot + off) = oh;
-                *reinterpret_cast<uint4*>(slot + p.a_plane + off) = ol;
+            const int h = h0 - 1 + r;
+            const bool row_ok = h >= 0 && h < p.H;
+            mbar_wait(smem_u32(&bar_sfull[ss]), sph);
+            if (row_ok) {
+              const uint8_t* stage = smem_raw + (s_base - smem_u32(smem_raw)) + (size_t)ss * kStageBytes;
+              const float fy = p.up_sh * h;
+              const float ly = fy - (float)(int)fy, hy = 1.f - ly;
+              const int rowb = kSrcPx * 64;
+              for (int item = tid; item < kSrcPx * 4; item += kInterpThreads) {
+                // staged layout: [plane hi,lo][source row y0,y1][kSrcPx pixels from xs][32 channels]
+                const int o = item * 16;
+                const bf16x8 ah = *reinterpret_cast<const uint4*>(stage + o);
+                const bf16x8 ch = *reinterpret_cast<const uint4*>(stage + rowb + o);
+                const bf16x8 al = *reinterpret_cast<const uint4*>(stage + 2 * rowb + o);
+                const bf16x8 cl = *reinterpret_cast<const uint4*>(stage + 3 * rowb + o);
+                float a[8], c[8];
+                unpack8(ah, al, a);
+                unpack8(ch, cl, c);
+                v0[item] = make_float4(hy * a[0] + ly * c[0], hy * a[1] + ly * c[1], hy * a[2] + ly * c[2],
+                                       hy * a[3] + ly * c[3]);
+                v1[item] = make_float4(hy * a[4] + ly * c[4], hy * a[5] + ly * c[5], hy * a[6] + ly * c[6],
+                                       hy * a[7] + ly * c[7]);
               }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
-              asm volatile("bar.sync 1, 256;" ::: "memory");
-              if (tid == 0) mbar_arrive(smem_u32(&bar_afull[as]));
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(kInterpThreads) : "memory");
+            if (tid == 0) mbar_arrive(smem_u32(&bar_sempty[ss]));   // the staged source rows are consumed
+            mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
+            uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * p.a_slot;
+            for (int item = tid; item < kRowPx * 4; item += kInterpThreads) {
+              const int q = item >> 2, j = item & 3;          // pixel of the slot, 8-channel group
+              const int w = w0 - 1 + q;
+              bf16x8 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
+              if (row_ok && w >= 0 && w < p.W) {
+                const float fx = p.up_sw * w;
+                const int x0 = (int)fx;
+                const int x1 = x0 + (x0 < p.xW - 1 ? 1 : 0);
+                const float lx = fx - x0, hx = 1.f - lx;
+                const int i0 = (x0 - xs) * 4 + j, i1 = (x1 - xs) * 4 + j;
+                const float4 pa = v0[i0], pb = v1[i0], qa = v0[i1], qb = v1[i1];
+                float y[8];
+                y[0] = hx * pa.x + lx * qa.x; y[1] = hx * pa.y + lx * qa.y;
+                y[2] = hx * pa.z + lx * qa.z; y[3] = hx * pa.w + lx * qa.w;
+                y[4] = hx * pb.x + lx * qb.x; y[5] = hx * pb.y + lx * qb.y;
+                y[6] = hx * pb.z + lx * qb.z; y[7] = hx * pb.w + lx * qb.w;
+                split8(y, oh, ol);
+              }
+              // SWIZZLE_64B (same pattern TMA writes and UMMA reads): 16-byte chunk j of 64-byte row q sits at
+              // chunk j ^ ((q >> 1) & 3) because the XOR takes address bits [7,9) and the slot is 1 KiB aligned
+              const int off = q * 64 + ((j ^ ((q >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(slot + off) = oh;
+              *reinterpret_cast<uint4*>(slot + p.a_plane + off) = ol;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
+            asm volatile("bar.sync 1, %0;" ::"n"(kInterpThreads) : "memory");
+            if (tid == 0) mbar_arrive(smem_u32(&bar_afull[as]));
             if (++as == p.n_uslots) {
               as = 0;
               aph ^= 1u;
+            }
+            if (++ss == kStages) {
+              ss = 0;
+              sph ^= 1u;
             }
           }
         }
@@ -504,6 +562,27 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     p.up_sh = in.H > 1 ? (float)(up_src->H - 1) / (float)(in.H - 1) : 0.f;   // as launch_upsample2x
     p.up_sw = in.W > 1 ? (float)(up_src->W - 1) / (float)(in.W - 1) : 0.f;
   }
+  CUtensorMap map_x;
+  if (up_src) {
+    // half-resolution source, unswizzled 32-channel x kSrcPx-pixel row boxes (read back by the interpolation warps)
+    cuuint64_t dims[5] = {(cuuint64_t)up_src->C, (cuuint64_t)up_src->W, (cuuint64_t)up_src->H, (cuuint64_t)up_src->N, 2};
+    const int64_t plane = (const char*)up_src->lo - (const char*)up_src->hi;
+    if (plane <= 0 || plane % 16) {
+      err = "tc_rows_launch: upsample source hi/lo planes must be 16-byte aligned with lo after hi";
+      return cudaErrorInvalidValue;
+    }
+    cuuint64_t strides[4] = {(cuuint64_t)up_src->sw * 2, (cuuint64_t)up_src->sh * 2, (cuuint64_t)up_src->sn * 2,
+                             (cuuint64_t)plane};
+    cuuint32_t box[5] = {32, (cuuint32_t)kSrcPx, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = tc_encode_fn()(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)up_src->hi, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      err = "cuTensorMapEncodeTiled(upsample source) failed for " + L.name + " code " + std::to_string((int)r);
+      return cudaErrorInvalidValue;
+    }
+  }
   static bool attr_set = false;
   static int num_sms = 0, max_smem = 0;
   if (!attr_set) {
@@ -511,11 +590,12 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048);
+    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 3072);
     cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_set = true;
   }
-  p.n_aslots = (max_smem - 2048 - 1024 - 2 * p.b_buf_bytes) / p.a_slot;
+  const int stage_bytes = p.up_chunks > 0 ? kStages * kStageBytes + kSrcPx * 128 : 0;
+  p.n_aslots = (max_smem - 3072 - 1024 - 2 * p.b_buf_bytes - stage_bytes) / p.a_slot;
   if (p.n_aslots > kMaxASlots) p.n_aslots = kMaxASlots;
   if (dual) p.n_aslots = 2;
   if (p.n_aslots < 2) {
@@ -523,10 +603,11 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     return cudaErrorInvalidValue;
   }
   p.n_uslots = p.up_chunks > 0 ? p.n_aslots / 2 : 0;
-  const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + 1024;
+  if (p.up_chunks > 0 && g_tc_debug[4] >= 1 && g_tc_debug[4] <= p.n_aslots - 2) p.n_uslots = g_tc_debug[4];
+  const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + stage_bytes + 1024;
   const int ctas = dual ? 2 * num_sms : num_sms;
   const int grid = p.total_tiles < ctas ? p.total_tiles : ctas;
-  conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, p);
+  conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
   return cudaGetLastError();
 }
 

@@ -80,6 +80,8 @@ def load_library():
         lib.vr_debug_set(3, int(os.environ['VR_FLAT']))
     if os.environ.get('VR_FUSE_UP'):
         lib.vr_debug_set(5, int(os.environ['VR_FUSE_UP']))
+    if os.environ.get('VR_USLOTS'):
+        lib.vr_debug_set(4, int(os.environ['VR_USLOTS']))
     if os.environ.get('VR_NO_ROWS'):
         lib.vr_debug_set(1, int(os.environ['VR_NO_ROWS']))
     _lib = lib
