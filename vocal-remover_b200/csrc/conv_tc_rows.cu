@@ -56,6 +56,7 @@ struct RowsParams {
   int bo_mode;
   // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
   int up_chunks, xH, xW, xC;
+  int a_c_off;   // channel coordinate of chunk 0 in the TMA map (negative: the map holds only the skip tensor)
   int n_uslots;   // A slots [0, n_uslots) form the ring of the interpolation warps, [n_uslots, n_aslots) the TMA ring:
                   // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
                   // parity cannot tell 'two uses behind' from 'up to date')
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
             if (elect_one_sync()) {
               mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * p.KB * 2));
-              tma_load_5d(adst, &tmA, cc * p.KB, w0 - 1, h0 - 1 + r, n, 0, afull);
-              tma_load_5d(adst + (uint32_t)p.a_plane, &tmA, cc * p.KB, w0 - 1, h0 - 1 + r, n, 1, afull);
+              tma_load_5d(adst, &tmA, cc * p.KB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 0, afull);
+              tma_load_5d(adst + (uint32_t)p.a_plane, &tmA, cc * p.KB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 1, afull);
             }
             __syncwarp();
             if (++as == p.n_aslots) {
@@ -554,7 +555,11 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.bo_mode = g_tc_debug[0];
   p.up_chunks = 0; p.xH = p.xW = p.xC = 0; p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
   p.up_sh = p.up_sw = 0.f;
+  p.a_c_off = 0;
   if (up_src) {
+    // `in` is either the whole concat buffer (its first up_src->C channels are then never read) or only the skip
+    // tensor, which starts at reduction index up_src->C
+    if (in.C + up_src->C <= R.CinPadR) p.a_c_off = -up_src->C;
     p.up_chunks = up_src->C / 32;
     p.xH = up_src->H; p.xW = up_src->W; p.xC = up_src->C;
     p.x_hi = up_src->hi; p.x_lo = up_src->lo;

@@ -199,10 +199,17 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   }
   // lstm channel + 15 zero channels keep every slice 32-byte aligned (full-sector 256-bit epilogue stores); with the
   // fused decoder upsample the group is a whole 32-channel chunk so that chunks are either upsampled or skip data
-  const int lg = (g_tc_debug[5] == 1 && (2 * n) % 32 == 0) ? 32 : 16;
+  // When dec1's upsample is certain to be fused (tensor-core mode, row kernel with 32-channel chunks), the up(h, lstm)
+  // slice is never materialised: cat1 then holds ONLY the skip tensor e1, dense, so that the row kernel's TMA reads of
+  // it are contiguous (inside the wide concat buffer e1 was a 32..64-byte island per 160..256-byte pixel and the
+  // 256-byte L2 promotion over-fetched: 292 MB of DRAM reads for 134 MB of operands on stg1_low.dec1).
+  P.skip_only = cfg_.conv_mode == 0 && g_tc_debug[5] == 1 && g_tc_debug[1] == 0 && g_tc_debug[2] != 64 &&
+                (2 * n) % 32 == 0 && W % 128 == 0 && H % 8 == 0;
+  const int lg = P.skip_only ? 32 : 16;
   const int c1 = round_up(3 * n + lg, 16);
-  P.e1_off = 2 * n + lg;
-  P.cat1 = make_buffer(Nb, H, W, c1);
+  P.e1_off = 2 * n + lg;                       // position of e1 in dec1's reduction (weight) order
+  P.e1_coff = P.skip_only ? 0 : P.e1_off;      // position of e1 in the cat1 buffer
+  P.cat1 = make_buffer(Nb, H, W, P.skip_only ? round_up(n, 16) : c1);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
   // Feature maps that feed a 3x3 stride-1 convolution at W <= 64 carry zero pad pixels after every row (>= the
@@ -479,6 +486,10 @@ bool Engine::run_decoder(ConvLayer& L, const ActView& low, const Buffer& cat, in
   const ActView cat_all = cat.all(N);
   if (cfg_.conv_mode == 0 && L.tc && tc_supported(L, cat_all, out) && tc_can_fuse_upsample(L, cat_all, out, low))
     return run_conv(L, cat_all, out, s, &low);   // channels [0, low.C) of cat are produced inside the kernel
+  if (cat.C < low.C + 1) {
+    err = "internal: " + L.name + " was laid out for the fused upsample but the fused kernel is not available";
+    return false;
+  }
   ++launches;
   if (!ck(launch_upsample2x(low, cat.view(N, 0, cat.H, 0, low.C), s), "decoder upsample")) return false;
   return run_conv(L, cat_all, out, s);
@@ -488,7 +499,7 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
                          cudaStream_t side) {
   const int n = P.n, H = P.H;
   // encoders (lib/nets.py:27-31); each skip tensor is written straight into its decoder's concat buffer
-  ActView e1 = P.cat1.view(N, 0, H, P.e1_off, n);
+  ActView e1 = P.cat1.view(N, 0, H, P.e1_coff, n);
   if (!run_conv(P.enc1, in, e1, s)) return false;
   ActView e2 = P.cat2.view(N, 0, H / 2, 4 * n, 2 * n);
   if (!run_conv(P.enc_a[0], e1, P.t2.all(N), s) || !run_conv(P.enc_b[0], P.t2.all(N), e2, s)) return false;
@@ -541,6 +552,10 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
       // fused: the convolution reads d2 (incl. the LSTM channel) itself, so it simply waits for the side stream
       if (!ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join")) return false;
       return run_decoder(P.dec[3], P.d2.all(N), P.cat1, N, out, s);
+    }
+    if (P.skip_only) {
+      err = "internal: " + P.prefix + ".dec1 was laid out for the fused upsample but the fused kernel is not available";
+      return false;
     }
     ++launches;
     if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 0, 2 * n), P.cat1.view(N, 0, H, 0, 2 * n), s), "up1")) return false;

@@ -72,6 +72,8 @@ struct BaseNetPlan {
   int n = 0, H = 0, W = 0;
   ConvLayer enc1, enc_a[4], enc_b[4], aspp1, aspp2, aspp_d[3], bott, dec[4];   // dec[0]=dec4 .. dec[3]=dec1
   LstmPlan lstm;
+  bool skip_only = false;   // cat1 holds only e1 (dec1's upsample is fused into the row kernel)
+  int e1_coff = 0;          // channel offset of e1 inside cat1
   Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2;
   int e1_off = 0;   // channel offset of e1 inside cat1
 };
