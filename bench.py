@@ -36,9 +36,10 @@ UNIT = 'audio-s/s'
 SR = 44100
 SECONDS_PER_GPU = 240.0
 CONV_FLOP_PER_WINDOW = 135.714e9
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the 97 convolution launches of one 8-window forward, / 8
-# (ncu capture profiles/r01_launches_bench30s_final.csv); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
-CONV_DRAM_BYTES_PER_WINDOW = 1.225e9
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the tensor-core convolution launches of four 11-window
+# passes, / 44 (ncu capture profiles/r01_launches_bench30s_fused.csv, decoder upsample fused into dec1/dec2; the build
+# before that fusion moved 1.225 GB); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
+CONV_DRAM_BYTES_PER_WINDOW = 0.879e9
 
 
 def measured_peaks():
@@ -250,8 +251,8 @@ def run_gpu(args):
                           'bf16x3 split precision)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                 'traffic': CONV_DRAM_BYTES_PER_WINDOW * n_windows / world / max(1.0, tc_n),
-                'traffic_note': 'average DRAM bytes per convolution launch = 1.225 GB per window (ncu, '
-                                'profiles/r01_launches_bench30s_final.csv) x windows per rank / launches',
+                'traffic_note': 'average DRAM bytes per convolution launch = 0.879 GB per window (ncu, '
+                                'profiles/r01_launches_bench30s_fused.csv) x windows per rank / launches',
                 'peak_source': peak_src,
                 'note': 'achieved = algorithmic conv FLOPs (real channel counts, 1x per product; the kernel issues 3 '
                         'bf16 MMA passes per product) of %d launches / their summed CUDA-event time %.2f ms on rank '
