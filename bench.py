@@ -128,6 +128,11 @@ def cpu_reference_arm(steps, warmup, sample_seconds=18.0):
     return sample_seconds / dt, dt, cores, sample_seconds
 
 
+def workload_text(seconds, n_windows, batch):
+    return ('%d s 44.1 kHz stereo synthetic track (240 s per GPU, BASELINE configs[2]), %d windows of cropsize 256, '
+            'window batch %d; seeded synthetic checkpoint (lib/synth.py)' % (int(seconds), n_windows, batch))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -135,6 +140,9 @@ def run_reference(args):
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 1))
     val, dt, cores, secs = cpu_reference_arm(steps, warm)
+    seconds = args.seconds_per_gpu * max(1, args.gpus)
+    T = 1 + int(seconds * SR) // 1024
+    n_windows = (T + (128 - T % 128)) // 128
     sample = ('first %.0f s of the synthetic track (%d windows) per step, oracle port of inference.py:147-176 on CPU '
               'fp32, batchsize 4; %d timed steps after %d warm-up' % (secs, int(np.ceil((1 + secs * SR // 1024) / 128)),
                                                                       steps, warm))
@@ -142,7 +150,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': '4-min 44.1 kHz stereo synthetic track, cropsize 256 (bounded sample per step)'},
+        'config': {'workload': workload_text(seconds, n_windows, args.batch),
+                   'reference_arm': 'CPU fp32, batchsize 4 (reference default); each step is a bounded sample of this '
+                                    'workload, see cpu_baseline.sample'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -271,9 +281,7 @@ def run_gpu(args):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16x3 (split-bf16 operands hi+lo, 3 tcgen05 passes, fp32 accumulate); fft/lstm fp32',
             'data': 'synthetic',
-            'config': {'workload': '%d s 44.1 kHz stereo synthetic track (240 s per GPU, BASELINE configs[2]), %d '
-                                   'windows of cropsize 256, window batch %d; seeded synthetic checkpoint '
-                                   '(lib/synth.py)' % (int(seconds), n_windows, args.batch),
+            'config': {'workload': workload_text(seconds, n_windows, args.batch),
                        'l2': 'no flush needed: per-step working set (spectrogram %.0f MB + activations > 1 GB) exceeds '
                              'the 126 MB L2' % (2 * 1025 * T * 8 / 1e6),
                        'parallelism': ('window-sharded x%d: STFT / net / inverse STFT per rank span, 4-byte max all-reduce, 8 KB '
