@@ -37,6 +37,14 @@ def main():
             print('mode %-8s device-resident max |diff| vs single GPU: %.3g' % (mode, e), flush=True)
             ok = ok and e < 1e-5
     os.environ['VR_GATHER'] = 'sharded'
+    # --tta (inference.py:83-98): both passes sharded by the same frame spans, combined locally
+    ref_inst_t, ref_voc_t = sp.separate_wave(d_wave, tta=True)
+    for rep in range(2):
+        inst, voc = vr_dist.separate_wave(sp, d_wave, tta=True, world=world, rank=rank)
+    if rank == 0:
+        e = max((inst - ref_inst_t).abs().max().item(), (voc - ref_voc_t).abs().max().item())
+        print('mode sharded+tta device-resident max |diff| vs single GPU: %.3g' % e, flush=True)
+        ok = ok and e < 1e-5
     h_wave = torch.from_numpy(wave).pin_memory()
     Lo = ref_inst.shape[1]
     h_inst = torch.zeros((2, Lo)).pin_memory()

@@ -174,3 +174,49 @@ def test_artifact_weights_edge_cases():
     # because its run end is the last INDEX, which never equals the frame count (lib/spec_utils.py:66,83)
     w = spec_utils.artifact_weights(np.full(300, 0.5, np.float32))
     assert w[0] == 1.0 and w[150] == 1.0 and w[-1] == 0.0
+
+
+def _emulated_separate_windows(mag_pad_fn, T, pad_l, first, count, mask, frame_shift, accumulate, roi=128, crop=256):
+    """Frame arithmetic of vr_separate_windows (include/vr_b200.h) with a stand-in 'net': the mask of a window is a
+    pointwise function of its centre frames, which is enough to check WHICH frames land WHERE."""
+    for g in range(first, first + count):
+        win = mag_pad_fn(pad_l, g * roi, g * roi + crop)          # (bins, crop) of the padded, normalised |X|
+        m = np.tanh(win[:, (crop - roi) // 2:(crop + roi) // 2]) + 0.01 * (g % 3)   # window-dependent on purpose
+        for j in range(roi):
+            t = g * roi + j - frame_shift
+            if 0 <= t < T:
+                mask[:, t] = 0.5 * (mask[:, t] + m[:, j]) if accumulate else m[:, j]
+
+
+@pytest.mark.parametrize('T,world', [(431, 2), (431, 3), (1000, 4), (128, 2), (130, 8), (2049, 8)])
+def test_sharded_tta_plan_reproduces_the_unsharded_combine(T, world):
+    """lib/distributed.py TTA sharding: every rank's own mask frames equal the single-rank result of
+    Separator.separate_tta's two passes + average (inference.py:83-98)."""
+    from lib import distributed as D
+    rng = np.random.default_rng(T)
+    bins = 5
+    mag = rng.random((bins, T)).astype(np.float64)
+
+    def padded(pad_l, lo, hi):
+        out = np.zeros((bins, hi - lo))
+        for i, t in enumerate(range(lo - pad_l, hi - pad_l)):
+            if 0 <= t < T:
+                out[:, i] = mag[:, t]
+        return out
+
+    n_windows, roi = D.window_count(T, 256, 64)
+    ref = np.zeros((bins, T))
+    _emulated_separate_windows(padded, T, 64, 0, n_windows, ref, 0, 0)
+    _emulated_separate_windows(padded, T, 64 + roi // 2, 0, n_windows + 1, ref, roi // 2, 1)
+    covered = np.zeros(T, dtype=bool)
+    for rank in range(world):
+        first, count, roi_, f0, f1, a, b, k0, k1 = D.shard_plan(T, 256, 64, world, rank)
+        local = np.full((bins, T), np.nan)     # stale / foreign frames must never leak into the rank's span
+        if count > 0:
+            _emulated_separate_windows(padded, T, 64, first, count, local, 0, 0)
+            g0, c2 = D.tta_window_range(first, count, n_windows)
+            assert g0 + c2 <= n_windows + 1
+            _emulated_separate_windows(padded, T, 64 + roi // 2, g0, c2, local, roi // 2, 1)
+        assert np.array_equal(local[:, f0:f1], ref[:, f0:f1])
+        covered[f0:f1] = True
+    assert covered.all()

@@ -4,10 +4,13 @@ Windows of a track are independent given the global normaliser (inference.py:74;
 state is per window), so rank r owns a contiguous block of window indices and, with it, the
 corresponding frame span of everything else on the path:
 
-* default (``VR_GATHER=sharded``, needs hop == n_fft/2 and no TTA): every stage is sharded.  A rank computes the
+* default (``VR_GATHER=sharded``, needs hop == n_fft/2): every stage is sharded.  A rank computes the
   STFT of just the frames its windows read, max|X| over them (one 4-byte all-reduce gives the global normaliser),
   its masks, receives ONE halo mask frame (8 KB) from its right neighbour, and runs the masked inverse STFT +
-  overlap-add of its own output span.  In the device-resident form the overlap-add kernel stores that span
+  overlap-add of its own output span.  With ``tta`` (inference.py:83-98) the second, half-window-shifted pass is
+  sharded by the same frame spans: a rank runs the count+1 shifted windows that overlap its span and averages them
+  into its own mask frames, so the combine needs no exchange either; the STFT is then computed whole on every rank
+  (0.3 ms per 4 minutes) because the TTA normaliser is numpy's lexicographic complex max of the whole track.  In the device-resident form the overlap-add kernel stores that span
   straight into rank 0's stem buffers, which are mapped into every rank through CUDA IPC (compute + gather in one
   kernel over NVLink); in the host form every rank moves only its own slice over PCIe.
 * ``VR_GATHER=p2p``: only the net is sharded; the mask epilogue kernel stores into rank 0's mask buffer over
@@ -92,16 +95,18 @@ def _shared_buffer(ctx, tag, nbytes, world, rank, dev, group):
 
 def separate_wave(sp, d_wave, tta=False, world=1, rank=0, group=None):
     """CUDA wave (2, L) on every rank -> (inst, voc) CUDA waves on rank 0 (None elsewhere)."""
-    if tta and world > 1:
-        raise NotImplementedError('multi-GPU --tta: shard files instead (SURVEY 8(f) rank 3)')
     if world == 1:
         return sp.separate_wave(d_wave, tta=tta)
     mode = os.environ.get('VR_GATHER', 'sharded')
     n_windows, _ = window_count(1 + d_wave.shape[1] // sp.model.hop_length, sp.cropsize, sp.offset)
     if mode == 'sharded' and (sp.model.hop_length * 2 != sp.model.n_fft or n_windows < world):
         mode = 'p2p'
+    if tta and mode != 'sharded':
+        # the TTA combine is a read-modify-write of the mask: it stays local to the rank that owns the frames
+        raise NotImplementedError('multi-GPU --tta needs the sharded mode (VR_GATHER=sharded, hop == n_fft/2, '
+                                  'at least one window per rank)')
     if mode == 'sharded':
-        return _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0=True)
+        return _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0=True, tta=tta)
     if mode == 'p2p':
         return _separate_wave_p2p(sp, d_wave, world, rank, group)
     return _separate_wave_nccl(sp, d_wave, world, rank, group)
@@ -123,7 +128,16 @@ def shard_plan(n_frames, cropsize, offset, world, rank):
     return first, count, roi, f0, f1, a, b, k0, k1
 
 
-def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=None):
+def tta_window_range(first, count, n_windows):
+    """Windows [g0, g0+c) of the shifted second TTA pass (inference.py:91-96) that overlap the mask frames of first-pass
+    windows [first, first+count): shifted window g covers track frames [roi*g - roi/2, roi*g + roi/2), and the pass
+    has n_windows + 1 windows."""
+    if count <= 0:
+        return first, 0
+    return first, min(count + 1, n_windows + 1 - first)
+
+
+def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=None, tta=False):
     """Everything sharded (see module docstring).  ``to_rank0``: stems are assembled in rank 0's HBM by the
     overlap-add kernels (returns them on rank 0); otherwise each rank writes its span into ``local_out``."""
     import torch.distributed as dist
@@ -143,16 +157,32 @@ def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=N
                             torch.empty((2, bins, T), dtype=torch.float32, device=dev))
         spec, mask = _shared[key]
         norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        if b > a:
-            ctx.check(ctx.lib.vr_stft_range(ctx.handle, _native.ptr(d_wave), L, _native.ptr(spec), T, a, b, st),
-                      'vr_stft_range')
-            ctx.check(ctx.lib.vr_normaliser_range(ctx.handle, _native.ptr(spec), T, a, b, _native.ptr(norm), st),
-                      'vr_normaliser_range')
-        dist.all_reduce(norm, op=dist.ReduceOp.MAX, group=group)        # inference.py:74, 4 bytes
+        if tta:
+            # inference.py:87,94: the normaliser is |lexicographic complex max| of the whole (padded) track
+            ctx.check(ctx.lib.vr_stft(ctx.handle, _native.ptr(d_wave), L, _native.ptr(spec), T, None, st), 'vr_stft')
+            ctx.check(ctx.lib.vr_normaliser(ctx.handle, _native.ptr(spec), T, 1, _native.ptr(norm), st),
+                      'vr_normaliser')
+        else:
+            if b > a:
+                ctx.check(ctx.lib.vr_stft_range(ctx.handle, _native.ptr(d_wave), L, _native.ptr(spec), T, a, b, st),
+                          'vr_stft_range')
+                ctx.check(ctx.lib.vr_normaliser_range(ctx.handle, _native.ptr(spec), T, a, b, _native.ptr(norm), st),
+                          'vr_normaliser_range')
+            dist.all_reduce(norm, op=dist.ReduceOp.MAX, group=group)        # inference.py:74, 4 bytes
         if count > 0:
             ctx.check(ctx.lib.vr_separate_windows(ctx.handle, _native.ptr(spec), T, _native.ptr(norm), sp.offset,
                                                   first, count, _native.ptr(mask), T, 0, 0, st),
                       'vr_separate_windows')
+            if tta:
+                # second pass, padded by a further roi/2 on the left: mask frame j of its concatenation is track
+                # frame j - roi/2, averaged into what the first pass left there ((old + new) / 2, inference.py:98).
+                # Its edge windows also touch roi/2 frames of the neighbours' spans in the LOCAL mask; those frames
+                # are never read here (the halo frame below is overwritten by the neighbour's value).
+                n_windows, _ = window_count(T, sp.cropsize, sp.offset)
+                g0, c2 = tta_window_range(first, count, n_windows)
+                ctx.check(ctx.lib.vr_separate_windows(ctx.handle, _native.ptr(spec), T, _native.ptr(norm),
+                                                      sp.offset + roi // 2, g0, c2, _native.ptr(mask), T, roi // 2, 1,
+                                                      st), 'vr_separate_windows (tta)')
         # halo: output hop k needs frames k and k+1, so the last hop of this span needs the first mask frame of
         # the right neighbour
         ops = []
