@@ -159,6 +159,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def write_layer_table(ctx, path):
+    """Per-layer CUDA-event times of the profiled step (vr_profile_dump), summed over its launches."""
+    import collections
+    import ctypes
+    need = ctypes.c_int64(0)
+    ctx.check(ctx.lib.vr_profile_dump(ctx.handle, None, 0, ctypes.byref(need)), 'vr_profile_dump')
+    buf = ctypes.create_string_buffer(need.value)
+    ctx.check(ctx.lib.vr_profile_dump(ctx.handle, buf, need.value, None), 'vr_profile_dump')
+    agg = collections.OrderedDict()
+    for ln in buf.value.decode().splitlines():
+        name, n, h, w, tc, ms, gf = ln.split()
+        key = (name, int(h), int(w), int(tc))
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += float(ms)
+        a[2] += float(gf)
+    total = sum(a[1] for a in agg.values()) or 1.0
+    with open(path, 'w') as f:
+        f.write('layer\tHout\tWout\ttensor_core\tlaunches\tms\tshare\tGFLOP\tTFLOP/s\n')
+        for (name, h, w, tc), (cnt, ms, gf) in agg.items():
+            f.write('%s\t%d\t%d\t%d\t%d\t%.4f\t%.4f\t%.3f\t%.1f\n' % (name, h, w, tc, cnt, ms, ms / total, gf,
+                                                                      gf / ms if ms > 0 else 0.0))
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import inference
@@ -229,6 +253,8 @@ def run_gpu(args):
     ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 1), 'vr_profile_enable')
     prof_ms = timed(step_device, 1)
     ctx.check(ctx.lib.vr_profile_read(ctx.handle, prof), 'vr_profile_read')
+    if args.layers and rank == 0:
+        write_layer_table(ctx, args.layers)
     ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 0), 'vr_profile_enable')
 
     # ---- end to end through the public host-buffer API (pinned host wave -> pinned host stems) ----
@@ -312,6 +338,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--batch', type=int, default=27, help='windows per forward launch sequence (240 s = 81 windows = 3 x 27)')
+    ap.add_argument('--layers', type=str, default='', help='write the per-layer conv timing table of the profiled '
+                                                           'step to this file')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU arm (profiling runs only)')
     ap.add_argument('--seconds-per-gpu', type=float, default=SECONDS_PER_GPU,
                     help='track length per GPU (default 240 s = BASELINE configs[2]; shorter only for profiling)')

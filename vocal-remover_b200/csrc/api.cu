@@ -244,6 +244,19 @@ int vr_profile_read(vr_ctx* ctx, double* out6) {
   return done(ctx, ctx->eng->profile_read(out6));
 }
 
+int vr_profile_dump(vr_ctx* ctx, char* text, int64_t cap, int64_t* needed) {
+  CHECK_CTX(ctx);
+  std::string t;
+  if (!ctx->eng->profile_dump(t)) return done(ctx, false);
+  if (needed) *needed = (int64_t)t.size() + 1;
+  if (text && cap > 0) {
+    const size_t n = t.size() < (size_t)cap - 1 ? t.size() : (size_t)cap - 1;
+    memcpy(text, t.data(), n);
+    text[n] = 0;
+  }
+  return 0;
+}
+
 int vr_debug_conv(vr_ctx* ctx, const float* x, int32_t N, int32_t Cin, int32_t H, int32_t W, const float* w,
                   const float* bias, int32_t Cout, int32_t k, int32_t stride, int32_t dil_h, int32_t dil_w, int32_t act,
                   int32_t use_tc, float* y, void* stream) {

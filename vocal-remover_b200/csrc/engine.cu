@@ -442,6 +442,20 @@ bool Engine::profile_read(double* out6) {
   return true;
 }
 
+bool Engine::profile_dump(std::string& text) {
+  text.clear();
+  char line[256];
+  for (auto& r : prof_) {
+    if (!ck(cudaEventSynchronize(r.b), "profile sync")) return false;
+    float ms = 0.f;
+    if (!ck(cudaEventElapsedTime(&ms, r.a, r.b), "profile elapsed")) return false;
+    snprintf(line, sizeof(line), "%s %d %d %d %d %.6f %.6f\n", r.name.c_str(), r.N, r.H, r.W, r.tc, (double)ms,
+             r.flops * 1e-9);
+    text += line;
+  }
+  return true;
+}
+
 bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src) {
   ++launches;
   const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
@@ -452,6 +466,8 @@ bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaS
     rec.tc = use_tc ? 1 : 0;
     // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
     rec.flops = 2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k;
+    rec.name = up_src ? L.name + "+up" : L.name;
+    rec.N = out.N; rec.H = out.H; rec.W = out.W;
     cudaEventRecord(rec.a, s);
   }
   bool ok = run_conv_inner(L, in, out, use_tc, s, up_src);

@@ -131,6 +131,7 @@ class Engine {
   // sums over the events recorded since enable: [0] tensor-core conv ms, [1] tensor-core conv algorithmic FLOPs,
   // [2] tensor-core launches, [3] CUDA-core conv ms, [4] CUDA-core conv FLOPs, [5] CUDA-core launches
   bool profile_read(double* out6);
+  bool profile_dump(std::string& text);   // one line per profiled launch: name N H W tc ms gflop
 
  private:
   Config cfg_;
@@ -138,7 +139,7 @@ class Engine {
   std::map<std::string, HostTensor> sd_;
   std::vector<void*> allocs_;
   int last_n_ = 0;
-  struct ProfRec { cudaEvent_t a, b; double flops; int tc; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int tc; std::string name; int N, H, W; };
   bool profiling_ = false;
   std::vector<ProfRec> prof_;
 

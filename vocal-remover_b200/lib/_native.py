@@ -48,6 +48,7 @@ SIGNATURES = {
     'vr_launch_count': (c_i64, [c_vp]),
     'vr_profile_enable': (c_i32, [c_vp, c_i32]),
     'vr_profile_read': (c_i32, [c_vp, ctypes.POINTER(ctypes.c_double)]),
+    'vr_profile_dump': (c_i32, [c_vp, ctypes.c_char_p, c_i64, ctypes.POINTER(c_i64)]),
     'vr_debug_conv': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_i32, c_i32, c_fp, c_vp]),
     'vr_debug_decoder': (c_i32, [c_vp, c_fp, c_i32, c_i32, c_i32, c_i32, c_fp, c_i32, c_fp, c_fp, c_i32, c_i32, c_i32,
