@@ -34,7 +34,7 @@ namespace vr {
 
 static constexpr int kInterpThreads = 288;          // 9 warps: 520 slot items in two passes, 272 source items in one
 static constexpr int kRowsThreads = 192 + kInterpThreads;   // TMA, MMA, 4 epilogue warps + the interpolation warps
-static constexpr int kMaxR = 8;                    // output rows per CTA tile (runtime: 8, or 4 with two CTAs per SM)
+static constexpr int kMaxR = 8;                    // output rows per CTA tile
 static constexpr int kRowPx = 130;                 // 128 + 2 halo pixels
 static constexpr int kMaxASlots = 8;
 static constexpr int kSrcPx = 68;                  // half-resolution pixels staged per source row (fused upsample)
@@ -53,7 +53,6 @@ struct RowsParams {
   int osw;
   const float* bias;
   int tmem_cols;
-  int bo_mode;
   // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
   int up_chunks, xH, xW, xC;
   int a_c_off;   // channel coordinate of chunk 0 in the TMA map (negative: the map holds only the skip tensor)
@@ -533,10 +532,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   }
   RowsParams p;
   p.N = out.N; p.H = out.H; p.W = out.W;
-  // g_tc_debug[4] = 1: two CTAs per SM (4 rows per tile, 32-channel chunks, 2 row slots, <= 256 TMEM columns each)
-  // so that two MMA-issuing threads feed the tensor pipe; needs the 32-channel chunk layout
-  const bool dual = false;   // two CTAs per SM measured neutral and no longer fits next to the interpolation warps
-  p.R = dual ? 4 : kMaxR;
+  p.R = kMaxR;
   p.tiles_w = out.W / 128; p.tiles_h = out.H / p.R; p.n_tiles = R.n_tiles;
   p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
   p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.BN = R.BN; p.Cout = L.Cout; p.act = L.act;
@@ -552,7 +548,6 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
   p.bias = R.bias;
   p.tmem_cols = 2 * p.R * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
-  p.bo_mode = g_tc_debug[0];
   p.up_chunks = 0; p.xH = p.xW = p.xC = 0; p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
   p.up_sh = p.up_sw = 0.f;
   p.a_c_off = 0;
@@ -602,7 +597,6 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   const int stage_bytes = p.up_chunks > 0 ? kStages * kStageBytes + kSrcPx * 128 : 0;
   p.n_aslots = (max_smem - 3072 - 1024 - 2 * p.b_buf_bytes - stage_bytes) / p.a_slot;
   if (p.n_aslots > kMaxASlots) p.n_aslots = kMaxASlots;
-  if (dual) p.n_aslots = 2;
   if (p.n_aslots < 2) {
     err = "tc_rows_launch: shared memory too small";
     return cudaErrorInvalidValue;
@@ -610,8 +604,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.n_uslots = p.up_chunks > 0 ? p.n_aslots / 2 : 0;
   if (p.up_chunks > 0 && g_tc_debug[4] >= 1 && g_tc_debug[4] <= p.n_aslots - 2) p.n_uslots = g_tc_debug[4];
   const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + stage_bytes + 1024;
-  const int ctas = dual ? 2 * num_sms : num_sms;
-  const int grid = p.total_tiles < ctas ? p.total_tiles : ctas;
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;   // persistent: one CTA per SM
   conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
   return cudaGetLastError();
 }
