@@ -10,8 +10,8 @@ pad_mode='constant', win_length=n_fft) as summarised in SURVEY.md App. A.
 
 PARITY UNPINNED at this boundary: the reference holds no tests / golden vectors
 for STFT, and librosa itself cannot be run here.  The restatement is cross-checked
-against an independent implementation (``torch.stft`` / ``torch.istft``) and by
-round trip in tests/test_oracle_stft.py.
+against two independent implementations (``torch.stft`` / ``torch.istft`` and
+``scipy.signal.stft`` / ``istft``) and by round trip in tests/test_oracle_stft.py.
 """
 import numpy as np
 

@@ -52,3 +52,22 @@ def test_golden_spectrogram(golden_default):
     S = stft_oracle.wave_to_spectrogram(x, 1024, 2048)
     assert np.array_equal(S[:, ::16, :], g['X_sub'])
     assert np.float32(np.abs(S).max()) == g['absmax']
+
+
+def test_stft_and_istft_match_scipy_signal():
+    """Second independent implementation (scipy.signal, the library librosa builds its window on): same framing
+    (zero centre padding, hop 1024, periodic Hann), scipy scales the forward transform by 1 / sum(window)."""
+    from scipy import signal
+    x = synth.sine_mix(2.0)
+    S = stft_oracle.wave_to_spectrogram(x, 1024, 2048)
+    win = signal.get_window('hann', 2048, fftbins=True)
+    _, _, Z = signal.stft(x.astype(np.float64), window=win, nperseg=2048, noverlap=1024, boundary='zeros',
+                          padded=False, return_onesided=True)
+    Z = Z * win.sum()
+    assert Z.shape == S.shape
+    assert np.abs(S - Z).max() <= 2e-5 * np.abs(Z).max()
+    _, w = signal.istft(S.astype(np.complex128) / win.sum(), window=win, nperseg=2048, noverlap=1024, boundary=True)
+    wo = stft_oracle.spectrogram_to_wave(S, 1024)
+    n = wo.shape[1]
+    assert w.shape[1] >= n
+    assert np.abs(wo - w[:, :n]).max() < 5e-6
