@@ -332,3 +332,25 @@ def test_postprocess_device_matches_host_merge_artifacts(default_model):
     a = sp.separate_wave(wave)[0]
     b = inference.Separator(default_model, _dev(), 4, 256, False).separate_wave(wave)[0]
     assert np.abs(a - b).max() < 1e-6
+
+
+@pytest.mark.skipif(__import__('os').environ.get('VR_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in switches that have not had their first GPU run (set VR_TEST_EXPERIMENTAL=1)')
+def test_zero_weight_group_skipping_is_exact(default_model, wave10):
+    """VR_KSKIP (g_tc_debug[6]): the row kernel does not issue MMAs / interpolation for 8-channel input groups whose
+    weights are all zero (lstm and pad groups of the concat layouts).  Skipped products are exact zeros, so the mask
+    must not change by a single bit."""
+    import inference
+    from lib import _native
+    from oracle import stft_oracle
+    X = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
+    sp = inference.Separator(default_model, _dev(), 4, 256, False)
+    d_spec = torch.from_numpy(X).cuda()
+    lib = _native.load_library()
+    base = sp._mask_device(d_spec, False).clone()
+    lib.vr_debug_set(6, 1)
+    try:
+        skipped = sp._mask_device(d_spec, False).clone()
+    finally:
+        lib.vr_debug_set(6, 0)
+    assert torch.equal(base, skipped)

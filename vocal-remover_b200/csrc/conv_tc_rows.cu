@@ -55,6 +55,7 @@ struct RowsParams {
   int tmem_cols;
   // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
   int up_chunks, xH, xW, xC;
+  unsigned long long kmask;   // bit g: some weight on input channels [8g, 8g+8) is non-zero (all ones = no skipping)
   int a_c_off;   // channel coordinate of chunk 0 in the TMA map (negative: the map holds only the skip tensor)
   int n_uslots;   // A slots [0, n_uslots) form the ring of the interpolation warps, [n_uslots, n_aslots) the TMA ring:
                   // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
@@ -65,6 +66,13 @@ struct RowsParams {
   int xsw;
   float up_sh, up_sw;
 };
+
+// 8-channel groups of chunk cc that carry any non-zero weight (4 bits for 32-channel chunks, 8 for 64)
+__device__ __forceinline__ uint32_t chunk_groups(unsigned long long kmask, int cc, int KB) {
+  const int gpc = KB >> 3, sh = cc * gpc;
+  const uint32_t full = (1u << gpc) - 1u;
+  return sh + gpc <= 64 ? (uint32_t)(kmask >> sh) & full : full;
+}
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -212,6 +220,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
           mbar_wait(smem_u32(&bar_bfull[bs]), bph);
           const uint32_t bsrc = b_base + (uint32_t)(bs * p.b_buf_bytes);
           const bool up = cc < p.up_chunks;
+          // k-steps (16 channels = two groups) whose weights are all zero are not issued: exact, since the products
+          // would be 0 (lstm / pad channel groups of the concat layouts); chunk 0 always keeps k-step 0 (accumulator init)
+          const uint32_t gm = chunk_groups(p.kmask, cc, p.KB);
+          const uint32_t ksm = ((gm & 0x3u) ? 1u : 0u) | ((gm & 0xCu) ? 2u : 0u) | ((gm & 0x30u) ? 4u : 0u) |
+                               ((gm & 0xC0u) ? 8u : 0u);
           for (int r = 0; r < p.R + 2; ++r) {
             const int as = up ? as_u : as_t;
             mbar_wait(smem_u32(&bar_afull[as]), up ? aph_u : aph_t);
@@ -235,6 +248,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks >= p.ksteps) break;
+                  if (!((ksm >> ks) & 1u)) continue;
                   const uint32_t ao = ((uint32_t)kw * row_bytes + (uint32_t)(ks * 32)) >> 4;
                   const uint32_t ko = (uint32_t)((ks * 32) >> 4);
                   if (kw == 0 && ks == 0 && fresh) {
@@ -304,6 +318,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         const int h0 = (mt % p.tiles_h) * p.R;
         const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
         for (int cc = 0; cc < p.up_chunks; ++cc) {
+          const uint32_t gmask = chunk_groups(p.kmask, cc, 32);
           for (int r = 0; r < p.R + 2; ++r) {
             const int h = h0 - 1 + r;
             const bool row_ok = h >= 0 && h < p.H;
@@ -314,6 +329,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
               const float ly = fy - (float)(int)fy, hy = 1.f - ly;
               const int rowb = kSrcPx * 64;
               for (int item = tid; item < kSrcPx * 4; item += kInterpThreads) {
+                if (!((gmask >> (item & 3)) & 1u)) continue;   // channel group without weights: never read below
                 // staged layout: [plane hi,lo][source row y0,y1][kSrcPx pixels from xs][32 channels]
                 const int o = item * 16;
                 const bf16x8 ah = *reinterpret_cast<const uint4*>(stage + o);
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
               const int q = item >> 2, j = item & 3;          // pixel of the slot, 8-channel group
               const int w = w0 - 1 + q;
               bf16x8 oh = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
-              if (row_ok && w >= 0 && w < p.W) {
+              if (row_ok && w >= 0 && w < p.W && ((gmask >> j) & 1u)) {
                 const float fx = p.up_sw * w;
                 const int x0 = (int)fx;
                 const int x1 = x0 + (x0 < p.xW - 1 ? 1 : 0);
@@ -458,6 +474,17 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
           planes[((size_t)brows + row) * Ktot + k] = lo;
         }
   }
+  // which 8-channel input groups carry any weight at all (the lstm / pad groups of the concat layouts do not)
+  R.kmask = ~0ull;
+  if (R.CinPadR / 8 <= 64) {
+    R.kmask = 0x3ull;   // k-step 0 of chunk 0 initialises the accumulators: never skipped
+    for (int ci = 0; ci < L.CinPad; ++ci) {
+      bool any = false;
+      for (int t = 0; t < 9 && !any; ++t)
+        for (int co = 0; co < L.Cout && !any; ++co) any = L.w_host[((size_t)t * L.CinPad + ci) * L.CoutPad + co] != 0.f;
+      if (any) R.kmask |= 1ull << (ci / 8);
+    }
+  }
   std::vector<float> bias((size_t)rows, 0.f);
   for (int co = 0; co < L.Cout; ++co) bias[(size_t)co] = L.bias_host[(size_t)co];
   void* dw = nullptr;
@@ -551,6 +578,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.up_chunks = 0; p.xH = p.xW = p.xC = 0; p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
   p.up_sh = p.up_sw = 0.f;
   p.a_c_off = 0;
+  p.kmask = g_tc_debug[6] == 1 ? R.kmask : ~0ull;   // VR_KSKIP=1: skip all-zero-weight channel groups (opt-in)
   if (up_src) {
     // `in` is either the whole concat buffer (its first up_src->C channels are then never read) or only the skip
     // tensor, which starts at reduction index up_src->C

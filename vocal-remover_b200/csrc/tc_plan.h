@@ -14,6 +14,7 @@ typedef std::tuple<const void*, const void*, int, int, int, int> ViewKey;
 struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 128 == 0 (conv_tc_rows.cu)
   bool ok = false;
   int KB = 32, CinPadR = 0, chunks = 0, BN = 0, n_tiles = 0;
+  unsigned long long kmask = ~0ull;   // bit g: input channels [8g, 8g+8) carry a non-zero weight
   bf16* w_planes = nullptr;   // [2][n_tiles*BN][9*CinPadR]
   float* bias = nullptr;      // [n_tiles*BN]
   CUtensorMap map_b;
@@ -53,6 +54,6 @@ bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err);
 bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_flat_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err);
-extern int g_tc_debug[8];   // [0] unused, [1] disable the row kernel, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = k: k of the row slots feed the interpolation warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel
+extern int g_tc_debug[8];   // [0] unused, [1] disable the row kernel, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = k: k of the row slots feed the interpolation warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1: the row kernel skips channel groups whose weights are all zero
 
 }  // namespace vr
