@@ -336,10 +336,12 @@ def test_postprocess_device_matches_host_merge_artifacts(default_model):
 
 @pytest.mark.skipif(__import__('os').environ.get('VR_TEST_EXPERIMENTAL') != '1',
                     reason='opt-in switches that have not had their first GPU run (set VR_TEST_EXPERIMENTAL=1)')
-def test_zero_weight_group_skipping_is_exact(default_model, wave10):
-    """VR_KSKIP (g_tc_debug[6]): the row kernel does not issue MMAs / interpolation for 8-channel input groups whose
-    weights are all zero (lstm and pad groups of the concat layouts).  Skipped products are exact zeros, so the mask
-    must not change by a single bit."""
+@pytest.mark.parametrize('knob', [6, 7])
+def test_optin_switches_are_exact(default_model, wave10, knob):
+    """g_tc_debug[6] (VR_KSKIP): the row kernel does not issue MMAs / interpolation for 8-channel input groups whose
+    weights are all zero (lstm and pad groups of the concat layouts) - the skipped products are exact zeros.
+    g_tc_debug[7] (VR_PDL): tensor-core convolutions launched with programmatic stream serialization - same work,
+    prologue overlapped with the previous kernel's tail.  Neither may change the mask by a single bit."""
     import inference
     from lib import _native
     from oracle import stft_oracle
@@ -348,9 +350,10 @@ def test_zero_weight_group_skipping_is_exact(default_model, wave10):
     d_spec = torch.from_numpy(X).cuda()
     lib = _native.load_library()
     base = sp._mask_device(d_spec, False).clone()
-    lib.vr_debug_set(6, 1)
+    lib.vr_debug_set(knob, 1)
     try:
-        skipped = sp._mask_device(d_spec, False).clone()
+        for _ in range(3):   # repeated: a missing dependency would show up as run-to-run differences
+            switched = sp._mask_device(d_spec, False).clone()
+            assert torch.equal(base, switched)
     finally:
-        lib.vr_debug_set(6, 0)
-    assert torch.equal(base, skipped)
+        lib.vr_debug_set(knob, 0)

@@ -44,6 +44,7 @@ struct TcParams {
   int osw;
   const float* bias;
   int tmem_cols;
+  int pdl;   // launched with programmatic stream serialization: wait for the producer grid after the prologue
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -89,6 +90,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (p.pdl) {
+    // everything above (barrier init, TMEM allocation, descriptor prefetch, bias: constants only) overlapped the tail
+    // of the previous kernel in the stream; its outputs may be read / this layer's outputs written only from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
@@ -468,6 +475,20 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  p.pdl = g_tc_debug[7] == 1 ? 1 : 0;   // VR_PDL=1 (opt-in)
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kThreads);
+    cfg.dynamicSmemBytes = (size_t)dyn;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel, it->second, tc.map_b, p);
+  }
   conv_tc_kernel<<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
   return cudaGetLastError();
 }

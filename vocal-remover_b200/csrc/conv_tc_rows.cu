@@ -56,6 +56,7 @@ struct RowsParams {
   // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
   int up_chunks, xH, xW, xC;
   unsigned long long kmask;   // bit g: some weight on input channels [8g, 8g+8) is non-zero (all ones = no skipping)
+  int pdl;       // launched with programmatic stream serialization (see conv_tc.cu)
   int a_c_off;   // channel coordinate of chunk 0 in the TMA map (negative: the map holds only the skip tensor)
   int n_uslots;   // A slots [0, n_uslots) form the ring of the interpolation warps, [n_uslots, n_aslots) the TMA ring:
                   // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
@@ -127,6 +128,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (p.pdl) {   // prologue overlapped the previous kernel's tail; activations may be touched only from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
@@ -633,6 +638,20 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   if (p.up_chunks > 0 && g_tc_debug[4] >= 1 && g_tc_debug[4] <= p.n_aslots - 2) p.n_uslots = g_tc_debug[4];
   const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + stage_bytes + 1024;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;   // persistent: one CTA per SM
+  p.pdl = g_tc_debug[7] == 1 ? 1 : 0;   // VR_PDL=1 (opt-in)
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kRowsThreads);
+    cfg.dynamicSmemBytes = (size_t)dyn;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_tc_rows_kernel, it->second, R.map_b, up_src ? map_x : it->second, p);
+  }
   conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
   return cudaGetLastError();
 }

@@ -54,6 +54,6 @@ bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err);
 bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_flat_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err);
-extern int g_tc_debug[8];   // [0] unused, [1] disable the row kernel, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = k: k of the row slots feed the interpolation warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1: the row kernel skips channel groups whose weights are all zero
+extern int g_tc_debug[8];   // [0] unused, [1] disable the row kernel, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = k: k of the row slots feed the interpolation warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1: the row kernel skips channel groups whose weights are all zero, [7] = 1: tensor-core convolutions are launched with programmatic stream serialization (prologue overlaps the previous kernel's tail)
 
 }  // namespace vr
