@@ -44,7 +44,6 @@ struct TcParams {
   int osw;
   const float* bias;
   int tmem_cols;
-  int pdl;   // launched with programmatic stream serialization: wait for the producer grid after the prologue
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -90,12 +89,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (p.pdl) {
-    // everything above (barrier init, TMEM allocation, descriptor prefetch, bias: constants only) overlapped the tail
-    // of the previous kernel in the stream; its outputs may be read / this layer's outputs written only from here on
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
@@ -257,7 +250,25 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 // ------------------------------------------------------------------------------------------------
 // host side
-int g_tc_debug[8] = {0, 0, 0, 0, 0, 1, 0, 0};   // [5] = 1: fused decoder upsample on by default
+int g_tc_debug[8] = {0, 0, 0, 0, 0, 1, 1, 0};   // [5] fused decoder upsample, [6] zero-weight group skipping: on
+
+static constexpr int kMaxDevices = 64;
+const TcDevice& tc_device() {
+  static TcDevice table[kMaxDevices];
+  static TcDevice none;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+  TcDevice& d = table[dev];
+  if (!d.ok) {
+    if (cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return none;
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - 2048);
+    tc_rows_set_attributes(d.max_smem);
+    d.ok = true;
+  }
+  return d;
+}
 
 EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -327,7 +338,7 @@ bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out) {
 bool tc_can_fuse_upsample(const ConvLayer& L, const ActView& in, const ActView& out, const ActView& up_src) {
   if (!L.tc || g_tc_debug[5] != 1) return false;
   const TcConv& tc = *L.tc;
-  if (!tc_rows_supported(L, tc, in, out) || tc.rows.KB != 32) return false;
+  if (!tc_rows_supported(L, tc, in, out)) return false;
   return up_src.C % 32 == 0 && up_src.C <= tc.rows.CinPadR && up_src.H * 2 == in.H && up_src.W * 2 == in.W &&
          up_src.sw % 8 == 0;
 }
@@ -387,7 +398,6 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
     return false;
   }
   if (!tc_rows_prepare(L, *tc, err, allocs)) return false;
-  if (!tc_flat_prepare(L, *tc, err)) return false;
   L.tc = tc;
   return true;
 }
@@ -400,7 +410,6 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
     err = "tc_launch: fused upsample is only implemented in the row-streaming kernel";
     return cudaErrorInvalidValue;
   }
-  if (tc_flat_supported(L, tc, in, out)) return tc_flat_launch(L, tc, in, out, s, err);
   const TileGeom g = tile_geom(out.H, out.W);
   auto key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
   auto it = tc.map_a.find(key);
@@ -441,14 +450,12 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   p.a_sub_bytes = 2 * p.a_plane_bytes;
   p.b_sub_bytes = 2 * p.b_plane_bytes;
   const int stage_bytes = tc.SUBS * (p.a_sub_bytes + p.b_sub_bytes);
-  static int max_smem = 0;
-  if (!max_smem) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048);
+  const TcDevice& dv = tc_device();
+  if (!dv.ok) {
+    err = "tc_launch: cannot query the current device";
+    return cudaErrorInvalidValue;
   }
-  const int dyn = max_smem - 2048;   // static barriers + staged bias live in the remaining 2 KiB
+  const int dyn = dv.max_smem - 2048;   // static barriers + staged bias live in the remaining 2 KiB
   p.stages = (dyn - 1024) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) {
@@ -467,28 +474,8 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   int cols = 32;
   while (cols < 4 * tc.BN) cols <<= 1;   // two accumulators x [D1 | D2]
   p.tmem_cols = cols;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  p.pdl = g_tc_debug[7] == 1 ? 1 : 0;   // VR_PDL=1 (opt-in)
-  if (p.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)kThreads);
-    cfg.dynamicSmemBytes = (size_t)dyn;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel, it->second, tc.map_b, p);
-  }
+  const int grid = total_tiles < dv.num_sms ? total_tiles : dv.num_sms;
   conv_tc_kernel<<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
   return cudaGetLastError();
 }

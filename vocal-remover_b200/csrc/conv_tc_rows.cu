@@ -4,26 +4,34 @@
 // by L2->SM bandwidth on the wide, shallow layers (enc1, enc2.conv2, dec2, dec1 of every BaseNet:
 // 69 % of the convolution time in profiles/r01_launches_bench30s_v1_direct.csv).  Here one CTA owns a
 // block of R=8 output rows x 128 pixels x BN couts with R accumulators resident in TMEM, and streams
-// the R+2 input rows it needs through shared memory ONCE per 64-channel chunk:
-//   * each input row (130 pixels incl. the +-1 halo, 64 channels, hi and lo plane) is one pair of TMA
+// the R+2 input rows it needs through shared memory ONCE per 32-channel chunk:
+//   * each input row (130 pixels incl. the +-1 halo, 32 channels, hi and lo plane) is one pair of TMA
 //     loads; out-of-image rows / columns are zero-filled by TMA = the conv padding;
 //   * a row feeds up to three output rows (kh = 0,1,2) and, for each, the three kw taps are the SAME
 //     shared-memory tile read through UMMA descriptors whose start address is shifted by kw pixels
-//     (+ kw * 128 B) - no data movement per tap.  Measured on B200 (tests/diag_rows.py): the 128B swizzle is
-//     applied to the absolute shared-memory address, so the shifted start needs NO matrix-base-offset
-//     (setting the field to (addr>>7)&7 produces garbage);
+//     (+ kw * 64 B) - no data movement per tap.  Measured on B200: the swizzle is applied to the absolute
+//     shared-memory address, so the shifted start needs NO matrix-base-offset (setting the field to
+//     (addr>>7)&7 produces garbage);
 //   * the weights of the three kh taps are STACKED along the MMA N dimension ([kh=2 | kh=1 | kh=0] x BN couts)
 //     and the R accumulators sit in adjacent TMEM columns, so ONE tcgen05.mma of N = 3*BN adds an input
-//     row's contribution to output rows r-2, r-1 and r at once: 3x fewer, 3x larger MMA instructions (with
-//     N = 16/32 the single issuing thread, not the tensor pipe, was the limit);
-//   * the 9-tap weight slab of the chunk (3 kw x [3*BN] x 64, hi+lo) is double-buffered in shared memory.
+//     row's contribution to output rows r-2, r-1 and r at once;
+//   * the 9-tap weight slab of the chunk (3 kw x [3*BN] x 32, hi+lo) is double-buffered in shared memory.
 // L2->SM traffic per output pixel drops from 9 to (R+2)/R = 1.25 operand fetches.
+//
+// MMA issue (round 2): everything the issuer adds to a descriptor inside a row is a compile-time constant (the
+// kernel is a template on BN; chunk width, slot and slab strides are constexpr).  With run-time strides ptxas kept
+// the descriptor arithmetic in vector registers and moved the operands of every UTCHMMA through R2UR: the row
+// kernel issued one MMA per 85-98 cycles whatever its N (profiles/r02_layers_before.tsv), i.e. the issuing thread
+// was the limit.  The micro-benchmark profiles/ubench/umma_issue.cu measures the same 18-MMA row with constant
+// offsets at 44 cycles per N=48 MMA and 56 per N=96 MMA - the shared-memory operand fetch of the tensor pipe,
+// (4096 + 32 N) bytes at 128 B/cycle, which is the next bound (N >= 128 is needed for N/2 cycles).
 //
 // Fused decoder upsample (optional, Decoder of lib/layers.py:51-64): the leading `up_chunks` channel chunks of the
 // input are F.interpolate(x2, bilinear, align_corners=True) of a tensor at half resolution.  Instead of reading a
-// materialised up-sampled copy (4x the bytes, and the decoder layers are HBM-bound), eight producer warps
-// interpolate each 130-pixel row straight from the low-resolution tensor into the swizzled operand slot
-// (generic-proxy stores + fence.proxy.async + mbarrier arrive), bit-identical to upsample2x_kernel.
+// materialised up-sampled copy (4x the bytes, and the decoder layers are HBM-bound), nine producer warps
+// interpolate each 130-pixel row from TMA-staged half-resolution rows into the swizzled operand slot
+// (generic-proxy stores + fence.proxy.async + mbarrier arrive), bit-identical to upsample2x_kernel up to the
+// order of the two blends.
 #include <stdio.h>
 
 #include "engine.h"
@@ -40,44 +48,117 @@ static constexpr int kMaxASlots = 8;
 static constexpr int kSrcPx = 68;                  // half-resolution pixels staged per source row (fused upsample)
 static constexpr int kStageBytes = 4 * kSrcPx * 64;   // {hi,lo} x {y0,y1} x kSrcPx x 32 channels
 static constexpr int kStages = 2;
+static constexpr uint32_t kKB = 32;                 // channels per chunk (SWIZZLE_64B rows of 64 bytes)
+static constexpr uint32_t kRowB = kKB * 2;          // bytes of one pixel of a chunk
+static constexpr uint32_t kAPlane = 9216;           // round_up(kRowPx * kRowB, 1024)
+static constexpr uint32_t kASlot = 2 * kAPlane;     // hi plane, lo plane
+
+template <int BN>
+struct RowsGeom {
+  static constexpr uint32_t kBPlane = 3 * BN * kRowB;   // hi -> lo plane inside one kw slab ([kh=2|kh=1|kh=0] x BN rows)
+  static constexpr uint32_t kBKw = 2 * kBPlane;         // one kw slab, both planes
+  static constexpr uint32_t kBBuf = 3 * kBKw;           // the three kw slabs of a chunk
+};
 
 struct RowsParams {
-  int N, H, W, R, tiles_w, tiles_h, n_tiles, total_tiles;
-  int chunks, CinPadR, BN, Cout, act;
-  int KB, ksteps, a_plane, a_slot, n_aslots, sbo, layout;   // channel-chunk width 64 (SW128) or 32 (SW64)
-  int b_kw_bytes, b_buf_bytes;
-  uint32_t idesc0;   // instruction descriptor without the N field
+  int N, H, W, tiles_w, tiles_h, n_tiles, total_tiles;
+  int chunks, CinPadR, Cout, act;
+  int n_aslots;
   bf16* out_hi;
   bf16* out_lo;
   int64_t osn, osh;
   int osw;
   const float* bias;
-  int tmem_cols;
   // fused bilinear x2 producer for the first up_chunks chunks (0: everything comes from the TMA map)
-  int up_chunks, xH, xW, xC;
+  int up_chunks, xH, xW;
   unsigned long long kmask;   // bit g: some weight on input channels [8g, 8g+8) is non-zero (all ones = no skipping)
-  int pdl;       // launched with programmatic stream serialization (see conv_tc.cu)
   int a_c_off;   // channel coordinate of chunk 0 in the TMA map (negative: the map holds only the skip tensor)
   int n_uslots;   // A slots [0, n_uslots) form the ring of the interpolation warps, [n_uslots, n_aslots) the TMA ring:
                   // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
                   // parity cannot tell 'two uses behind' from 'up to date')
-  const bf16* x_hi;
-  const bf16* x_lo;
-  int64_t xsn, xsh;
-  int xsw;
   float up_sh, up_sw;
 };
 
-// 8-channel groups of chunk cc that carry any non-zero weight (4 bits for 32-channel chunks, 8 for 64)
-__device__ __forceinline__ uint32_t chunk_groups(unsigned long long kmask, int cc, int KB) {
-  const int gpc = KB >> 3, sh = cc * gpc;
-  const uint32_t full = (1u << gpc) - 1u;
-  return sh + gpc <= 64 ? (uint32_t)(kmask >> sh) & full : full;
+// 8-channel groups of chunk cc that carry any non-zero weight (4 bits per 32-channel chunk)
+__device__ __forceinline__ uint32_t chunk_groups(unsigned long long kmask, int cc) {
+  const int sh = cc * 4;
+  return sh + 4 <= 64 ? (uint32_t)(kmask >> sh) & 0xFu : 0xFu;
 }
 
+// tcgen05.mma with the accumulate flag as a compile-time constant (UPT / !UPT in SASS)
+template <int ACC>
+__device__ __forceinline__ void umma_c(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t hi32, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo32), "r"(b_lo32), "r"(hi32), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+
+// The three split-precision products of one 16-channel k-step: hi*hi + lo*hi + hi*lo
+template <int BN, int ACC0>
+__device__ __forceinline__ void umma_triple(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t dhi,
+                                            uint32_t idesc) {
+  umma_c<ACC0>(d, a_hi, b_hi, dhi, idesc);
+  umma_c<1>(d, a_lo, b_hi, dhi, idesc);
+  umma_c<1>(d, a_hi, b_hi + (RowsGeom<BN>::kBPlane >> 4), dhi, idesc);
+}
+
+// All MMAs of one input row of one chunk.  KSM: k-steps (16 channels) of the chunk that carry weights (bit 0 / 1).
+// a_hi: descriptor low word of the slot's hi plane; b_row: low word of the weight rows of the first accumulator fed.
+template <int BN, int KSM>
+__device__ __forceinline__ void issue_row(uint32_t d, uint32_t a_hi, uint32_t b_row, uint32_t dhi, uint32_t idesc) {
+  const uint32_t a_lo = a_hi + (kAPlane >> 4);
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!((KSM >> ks) & 1)) continue;
+      const uint32_t ao = (uint32_t)(kw * kRowB + ks * 32) >> 4;
+      const uint32_t bo = (uint32_t)(kw * RowsGeom<BN>::kBKw + ks * 32) >> 4;
+      umma_triple<BN, 1>(d, a_hi + ao, a_lo + ao, b_row + bo, dhi, idesc);
+    }
+  }
+}
+
+// Same for a row that is the FIRST contribution to its newest accumulator (chunk 0, r < R): k-step 0 of tap kw = 0
+// overwrites that accumulator (accumulate = 0) and accumulates into the `cnt - 1` older ones.
+template <int BN, int KSM>
+__device__ __forceinline__ void issue_row_fresh(uint32_t d, uint32_t a_hi, uint32_t b_row, uint32_t dhi, uint32_t idesc0,
+                                                int cnt) {
+  const uint32_t a_lo = a_hi + (kAPlane >> 4);
+  const uint32_t n_old = (uint32_t)((cnt - 1) * BN);
+  const uint32_t idesc_new = idesc0 | ((uint32_t)(BN >> 3) << 17);
+  const uint32_t idesc_all = idesc0 | ((uint32_t)((cnt * BN) >> 3) << 17);
+  if (cnt > 1) {
+    const uint32_t idesc_old = idesc0 | ((n_old >> 3) << 17);
+    umma_triple<BN, 1>(d, a_hi, a_lo, b_row, dhi, idesc_old);
+  }
+  umma_triple<BN, 0>(d + n_old, a_hi, a_lo, b_row + ((n_old * kRowB) >> 4), dhi, idesc_new);
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      if ((kw == 0 && ks == 0) || !((KSM >> ks) & 1)) continue;
+      const uint32_t ao = (uint32_t)(kw * kRowB + ks * 32) >> 4;
+      const uint32_t bo = (uint32_t)(kw * RowsGeom<BN>::kBKw + ks * 32) >> 4;
+      umma_triple<BN, 1>(d, a_hi + ao, a_lo + ao, b_row + bo, dhi, idesc_all);
+    }
+  }
+}
+
+template <int BN>
 __global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmX, const RowsParams p) {
+  typedef RowsGeom<BN> G;
+  constexpr int R = kMaxR;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_afull[kMaxASlots];
   __shared__ __align__(8) uint64_t bar_aempty[kMaxASlots];
@@ -94,9 +175,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + (uint32_t)(p.n_aslots * p.a_slot);
-  const uint32_t s_base = b_base + (uint32_t)(2 * p.b_buf_bytes);
+  const uint32_t b_base = smem_base + (uint32_t)p.n_aslots * kASlot;
+  const uint32_t s_base = b_base + 2 * G::kBBuf;
   const uint32_t v_base = s_base + (uint32_t)(kStages * kStageBytes);   // fp32 vertically blended source row
+  constexpr uint32_t kTmemCols = 2 * R * BN;   // 512 (BN=32) or 256 (BN=16): powers of two
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -119,192 +201,170 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
+                 "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
+  for (int i = threadIdx.x; i < p.n_tiles * BN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (p.pdl) {   // prologue overlapped the previous kernel's tail; activations may be touched only from here on
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
-    {
-      int as = p.n_uslots, bs = 0, ss = 0;
-      uint32_t aph = 0, bph = 0, sph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
-        const int w0 = (mt % p.tiles_w) * 128;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.R;
-        const int n = mt / p.tiles_h;
-        for (int cc = 0; cc < p.chunks; ++cc) {
-          mbar_wait(smem_u32(&bar_bempty[bs]), bph ^ 1u);
-          const uint32_t bfull = smem_u32(&bar_bfull[bs]);
-          const uint32_t bdst = b_base + (uint32_t)(bs * p.b_buf_bytes);
-          if (elect_one_sync()) {
-            mbar_expect_tx(bfull, (uint32_t)(3 * p.b_kw_bytes));
+    int as = p.n_uslots, bs = 0, ss = 0;
+    uint32_t aph = 0, bph = 0, sph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int w0 = (mt % p.tiles_w) * 128;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * R;
+      const int n = mt / p.tiles_h;
+      for (int cc = 0; cc < p.chunks; ++cc) {
+        mbar_wait(smem_u32(&bar_bempty[bs]), bph ^ 1u);
+        const uint32_t bfull = smem_u32(&bar_bfull[bs]);
+        const uint32_t bdst = b_base + (uint32_t)bs * G::kBBuf;
+        if (elect_one_sync()) {
+          mbar_expect_tx(bfull, G::kBBuf);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              tma_load_3d(bdst + (uint32_t)(kw * p.b_kw_bytes), &tmB, kw * p.CinPadR + cc * p.KB, nt * 3 * p.BN, 0,
-                          bfull);
-          }
-          __syncwarp();
-          if (++bs == 2) {
-            bs = 0;
-            bph ^= 1u;
-          }
-          for (int r = 0; r < p.R + 2; ++r) {
-            if (cc < p.up_chunks) {
-              // rows of this chunk are produced by the interpolation warps; stage their two half-resolution source
-              // rows (hi and lo planes) in shared memory so that each source pixel crosses L2->SM once per row
-              mbar_wait(smem_u32(&bar_sempty[ss]), sph ^ 1u);
-              const uint32_t sfull = smem_u32(&bar_sfull[ss]);
-              const uint32_t sdst = s_base + (uint32_t)(ss * kStageBytes);
-              const int h = h0 - 1 + r;
-              if (elect_one_sync()) {
-                if (h >= 0 && h < p.H) {
-                  const float fy = p.up_sh * h;
-                  const int y0 = (int)fy;
-                  const int y1 = y0 + (y0 < p.xH - 1 ? 1 : 0);
-                  const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
-                  mbar_expect_tx(sfull, (uint32_t)kStageBytes);
-#pragma unroll
-                  for (int pl = 0; pl < 2; ++pl) {
-                    tma_load_5d(sdst + (uint32_t)((pl * 2 + 0) * kSrcPx * 64), &tmX, cc * 32, xs, y0, n, pl, sfull);
-                    tma_load_5d(sdst + (uint32_t)((pl * 2 + 1) * kSrcPx * 64), &tmX, cc * 32, xs, y1, n, pl, sfull);
-                  }
-                } else {
-                  mbar_arrive(sfull);   // halo row outside the image: the interpolation warps write zeros
-                }
-              }
-              __syncwarp();
-              if (++ss == kStages) {
-                ss = 0;
-                sph ^= 1u;
-              }
-              continue;
-            }
-            mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
-            const uint32_t afull = smem_u32(&bar_afull[as]);
-            const uint32_t adst = a_base + (uint32_t)(as * p.a_slot);
+          for (int kw = 0; kw < 3; ++kw)
+            tma_load_3d(bdst + (uint32_t)kw * G::kBKw, &tmB, kw * p.CinPadR + cc * (int)kKB, nt * 3 * BN, 0, bfull);
+        }
+        __syncwarp();
+        if (++bs == 2) {
+          bs = 0;
+          bph ^= 1u;
+        }
+        for (int r = 0; r < R + 2; ++r) {
+          if (cc < p.up_chunks) {
+            // rows of this chunk are produced by the interpolation warps; stage their two half-resolution source
+            // rows (hi and lo planes) in shared memory so that each source pixel crosses L2->SM once per row
+            mbar_wait(smem_u32(&bar_sempty[ss]), sph ^ 1u);
+            const uint32_t sfull = smem_u32(&bar_sfull[ss]);
+            const uint32_t sdst = s_base + (uint32_t)(ss * kStageBytes);
+            const int h = h0 - 1 + r;
             if (elect_one_sync()) {
-              mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * p.KB * 2));
-              tma_load_5d(adst, &tmA, cc * p.KB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 0, afull);
-              tma_load_5d(adst + (uint32_t)p.a_plane, &tmA, cc * p.KB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 1, afull);
+              if (h >= 0 && h < p.H) {
+                const float fy = p.up_sh * h;
+                const int y0 = (int)fy;
+                const int y1 = y0 + (y0 < p.xH - 1 ? 1 : 0);
+                const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
+                mbar_expect_tx(sfull, (uint32_t)kStageBytes);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                  tma_load_5d(sdst + (uint32_t)((pl * 2 + 0) * kSrcPx * 64), &tmX, cc * 32, xs, y0, n, pl, sfull);
+                  tma_load_5d(sdst + (uint32_t)((pl * 2 + 1) * kSrcPx * 64), &tmX, cc * 32, xs, y1, n, pl, sfull);
+                }
+              } else {
+                mbar_arrive(sfull);   // halo row outside the image: the interpolation warps write zeros
+              }
             }
             __syncwarp();
-            if (++as == p.n_aslots) {
-              as = p.n_uslots;
-              aph ^= 1u;
+            if (++ss == kStages) {
+              ss = 0;
+              sph ^= 1u;
             }
+            continue;
+          }
+          mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
+          const uint32_t afull = smem_u32(&bar_afull[as]);
+          const uint32_t adst = a_base + (uint32_t)as * kASlot;
+          if (elect_one_sync()) {
+            mbar_expect_tx(afull, (uint32_t)(2 * kRowPx * kRowB));
+            tma_load_5d(adst, &tmA, cc * (int)kKB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 0, afull);
+            tma_load_5d(adst + kAPlane, &tmA, cc * (int)kKB + p.a_c_off, w0 - 1, h0 - 1 + r, n, 1, afull);
+          }
+          __syncwarp();
+          if (++as == p.n_aslots) {
+            as = p.n_uslots;
+            aph ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
-    {
+    // ===================== MMA issuer: ONE elected lane runs the whole loop nest =====================
+    // The tensor pipe queues only a few MMAs, so every cycle the issuing thread spends between the last MMA of a row
+    // and the first MMA of the next one is a bubble in the pipe (measured: ~490 cycles of per-row scalar code made a
+    // 920-cycle row take 1440).  Hence: the row loop is fully unrolled (accumulator offsets, weight-row offsets and the
+    // N field of the instruction descriptor are immediates), per-chunk quantities are hoisted, and the lane election
+    // happens once per kernel instead of once per row.
+    if (elect_one_sync()) {
       int as_t = p.n_uslots, as_u = 0, bs = 0, acc = 0;
       uint32_t aph_t = 0, aph_u = 0, bph = 0, acc_phase = 0;
-      const uint32_t row_bytes = (uint32_t)(p.KB * 2);
-      const uint32_t b3_plane = (uint32_t)(3 * p.BN) * row_bytes;   // hi -> lo plane inside one kw slab
-      const uint32_t dhi = desc_hi((uint32_t)p.sbo, (uint32_t)p.layout);
+      const uint32_t dhi = desc_hi(8 * kRowB, 4u);   // SWIZZLE_64B, 8-row groups of 64-byte rows
+      // instruction descriptor without the N field: D=f32, A=B=bf16, K-major, M=128
+      constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t afull0 = smem_u32(&bar_afull[0]), aempty0 = smem_u32(&bar_aempty[0]);
+      const uint32_t a_lo0 = desc_lo(a_base);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_set = tmem_base + (uint32_t)(acc * p.R * p.BN);
+        const uint32_t d_set = tmem_base + (uint32_t)(acc * R * BN);
         for (int cc = 0; cc < p.chunks; ++cc) {
           mbar_wait(smem_u32(&bar_bfull[bs]), bph);
-          const uint32_t bsrc = b_base + (uint32_t)(bs * p.b_buf_bytes);
+          const uint32_t bsrc = desc_lo(b_base + (uint32_t)bs * G::kBBuf);
           const bool up = cc < p.up_chunks;
           // k-steps (16 channels = two groups) whose weights are all zero are not issued: exact, since the products
           // would be 0 (lstm / pad channel groups of the concat layouts); chunk 0 always keeps k-step 0 (accumulator init)
-          const uint32_t gm = chunk_groups(p.kmask, cc, p.KB);
-          const uint32_t ksm = ((gm & 0x3u) ? 1u : 0u) | ((gm & 0xCu) ? 2u : 0u) | ((gm & 0x30u) ? 4u : 0u) |
-                               ((gm & 0xC0u) ? 8u : 0u);
-          for (int r = 0; r < p.R + 2; ++r) {
-            const int as = up ? as_u : as_t;
-            mbar_wait(smem_u32(&bar_afull[as]), up ? aph_u : aph_t);
-            tc_fence_after();
-            const uint32_t a_hi = desc_lo(a_base + (uint32_t)(as * p.a_slot));
-            const uint32_t a_lo = desc_lo(a_base + (uint32_t)(as * p.a_slot + p.a_plane));
-            // input row r feeds output rows o = r-kh; accumulators o_lo..o_hi are adjacent TMEM column blocks
+          const uint32_t gm = chunk_groups(p.kmask, cc);
+          const uint32_t ksm = ((gm & 0x3u) ? 1u : 0u) | ((gm & 0xCu) ? 2u : 0u);
+          // this chunk's ring of A slots: the interpolation ring [0, n_uslots) or the TMA ring [n_uslots, n_aslots)
+          int as = up ? as_u : as_t;
+          uint32_t aph = up ? aph_u : aph_t;
+          const int ring_lo = up ? 0 : p.n_uslots, ring_hi = up ? p.n_uslots : p.n_aslots;
+#pragma unroll
+          for (int r = 0; r < R + 2; ++r) {
+            // input row r feeds output rows o = r-kh; accumulators o_lo..o_hi are adjacent TMEM column blocks; the
+            // weight rows are stacked [kh=2 | kh=1 | kh=0], the block of accumulator o_lo is kh = r - o_lo
+            constexpr int kR = R;
             const int o_lo = r - 2 < 0 ? 0 : r - 2;
-            const int o_hi = r > p.R - 1 ? p.R - 1 : r;
+            const int o_hi = r > kR - 1 ? kR - 1 : r;
             const int cnt = o_hi - o_lo + 1;
-            const uint32_t d_tmem = d_set + (uint32_t)(o_lo * p.BN);
-            // weight rows are stacked [kh=2 | kh=1 | kh=0]; block of accumulator o_lo is kh = r - o_lo
-            const uint32_t b_row0 = (uint32_t)((2 - (r - o_lo)) * p.BN) * row_bytes;
-            const uint32_t idesc_all = p.idesc0 | ((uint32_t)((cnt * p.BN) >> 3) << 17);
-            const bool fresh = cc == 0 && r <= p.R - 1;   // accumulator r receives its first product now
-            if (elect_one_sync()) {   // one elected lane issues the whole row
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const uint32_t bk_hi = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b_row0);
-                const uint32_t bk_lo = desc_lo(bsrc + (uint32_t)(kw * p.b_kw_bytes) + b3_plane + b_row0);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks >= p.ksteps) break;
-                  if (!((ksm >> ks) & 1u)) continue;
-                  const uint32_t ao = ((uint32_t)kw * row_bytes + (uint32_t)(ks * 32)) >> 4;
-                  const uint32_t ko = (uint32_t)((ks * 32) >> 4);
-                  if (kw == 0 && ks == 0 && fresh) {
-                    // first touch of accumulator r must overwrite: split the stacked MMA once
-                    const uint32_t n_old = (uint32_t)((cnt - 1) * p.BN);
-                    const uint32_t idesc_old = p.idesc0 | ((n_old >> 3) << 17);
-                    const uint32_t idesc_new = p.idesc0 | ((uint32_t)(p.BN >> 3) << 17);
-                    const uint32_t bn_off = ((uint32_t)((cnt - 1) * p.BN) * row_bytes) >> 4;
-                    if (cnt > 1) {
-                      umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_old, 1u);
-                      umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_old, 1u);
-                      umma_bf16_w(d_tmem, a_hi + ao, bk_lo + ko, dhi, idesc_old, 1u);
-                    }
-                    umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_hi + ko + bn_off, dhi, idesc_new, 0u);
-                    umma_bf16_w(d_tmem + n_old, a_lo + ao, bk_hi + ko + bn_off, dhi, idesc_new, 1u);
-                    umma_bf16_w(d_tmem + n_old, a_hi + ao, bk_lo + ko + bn_off, dhi, idesc_new, 1u);
-                  } else {
-                    umma_bf16_w(d_tmem, a_hi + ao, bk_hi + ko, dhi, idesc_all, 1u);
-                    umma_bf16_w(d_tmem, a_lo + ao, bk_hi + ko, dhi, idesc_all, 1u);
-                    umma_bf16_w(d_tmem, a_hi + ao, bk_lo + ko, dhi, idesc_all, 1u);
-                  }
-                }
-              }
-              umma_commit(smem_u32(&bar_aempty[as]));
+            const uint32_t d_tmem = d_set + (uint32_t)(o_lo * BN);
+            const uint32_t b_row = bsrc + (((uint32_t)((2 - (r - o_lo)) * BN) * kRowB) >> 4);
+            const uint32_t idesc_all = idesc0 | ((uint32_t)((cnt * BN) >> 3) << 17);
+            mbar_wait(afull0 + (uint32_t)as * 8u, aph);
+            const uint32_t a_hi = a_lo0 + (uint32_t)as * (kASlot >> 4);
+            if (cc == 0 && r <= kR - 1) {   // accumulator r receives its first product now
+              if (ksm == 3u) issue_row_fresh<BN, 3>(d_tmem, a_hi, b_row, dhi, idesc0, cnt);
+              else issue_row_fresh<BN, 1>(d_tmem, a_hi, b_row, dhi, idesc0, cnt);
+            } else if (ksm == 3u) {
+              issue_row<BN, 3>(d_tmem, a_hi, b_row, dhi, idesc_all);
+            } else if (ksm == 1u) {
+              issue_row<BN, 1>(d_tmem, a_hi, b_row, dhi, idesc_all);
+            } else if (ksm == 2u) {
+              issue_row<BN, 2>(d_tmem, a_hi, b_row, dhi, idesc_all);
             }
-            __syncwarp();
-            if (up) {
-              if (++as_u == p.n_uslots) {
-                as_u = 0;
-                aph_u ^= 1u;
-              }
-            } else {
-              if (++as_t == p.n_aslots) {
-                as_t = p.n_uslots;
-                aph_t ^= 1u;
-              }
+            umma_commit(aempty0 + (uint32_t)as * 8u);
+            if (++as == ring_hi) {
+              as = ring_lo;
+              aph ^= 1u;
             }
           }
-          if (elect_one_sync()) umma_commit(smem_u32(&bar_bempty[bs]));
+          if (up) {
+            as_u = as;
+            aph_u = aph;
+          } else {
+            as_t = as;
+            aph_t = aph;
+          }
+          umma_commit(smem_u32(&bar_bempty[bs]));
           if (++bs == 2) {
             bs = 0;
             bph ^= 1u;
           }
         }
-        if (elect_one_sync()) umma_commit(smem_u32(&bar_tfull[acc]));
+        umma_commit(smem_u32(&bar_tfull[acc]));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
     }
+    __syncwarp();
   } else if (warp >= 6) {
     // ===================== bilinear x2 producer (9 warps) =====================
     // Per A-slot row: (A) blend the two staged half-resolution source rows vertically into an fp32 row in shared
@@ -320,11 +380,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         int mt = tile / p.n_tiles;
         const int w0 = (mt % p.tiles_w) * 128;
         mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.R;
+        const int h0 = (mt % p.tiles_h) * R;
         const int xs = (int)(p.up_sw * (w0 > 0 ? w0 - 1 : 0));
         for (int cc = 0; cc < p.up_chunks; ++cc) {
-          const uint32_t gmask = chunk_groups(p.kmask, cc, 32);
-          for (int r = 0; r < p.R + 2; ++r) {
+          const uint32_t gmask = chunk_groups(p.kmask, cc);
+          for (int r = 0; r < R + 2; ++r) {
             const int h = h0 - 1 + r;
             const bool row_ok = h >= 0 && h < p.H;
             mbar_wait(smem_u32(&bar_sfull[ss]), sph);
@@ -353,7 +413,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             asm volatile("bar.sync 1, %0;" ::"n"(kInterpThreads) : "memory");
             if (tid == 0) mbar_arrive(smem_u32(&bar_sempty[ss]));   // the staged source rows are consumed
             mbar_wait(smem_u32(&bar_aempty[as]), aph ^ 1u);
-            uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * p.a_slot;
+            uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * kASlot;
             for (int item = tid; item < kRowPx * 4; item += kInterpThreads) {
               const int q = item >> 2, j = item & 3;          // pixel of the slot, 8-channel group
               const int w = w0 - 1 + q;
@@ -376,7 +436,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
               // chunk j ^ ((q >> 1) & 3) because the XOR takes address bits [7,9) and the slot is 1 KiB aligned
               const int off = q * 64 + ((j ^ ((q >> 1) & 3)) << 4);
               *reinterpret_cast<uint4*>(slot + off) = oh;
-              *reinterpret_cast<uint4*>(slot + p.a_plane + off) = ol;
+              *reinterpret_cast<uint4*>(slot + kAPlane + off) = ol;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
             asm volatile("bar.sync 1, %0;" ::"n"(kInterpThreads) : "memory");
@@ -405,33 +465,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       int mt = tile / p.n_tiles;
       const int w0 = (mt % p.tiles_w) * 128;
       mt /= p.tiles_w;
-      const int h0 = (mt % p.tiles_h) * p.R;
+      const int h0 = (mt % p.tiles_h) * R;
       const int n = mt / p.tiles_h;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t t_set = tmem_base + (uint32_t)(acc * p.R * p.BN) + ((uint32_t)(q * 32) << 16);
-      for (int orow = 0; orow < p.R; ++orow) {
+      const uint32_t t_set = tmem_base + (uint32_t)(acc * R * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int orow = 0; orow < R; ++orow) {
         const int64_t obase = (int64_t)n * p.osn + (int64_t)(h0 + orow) * p.osh + (int64_t)(w0 + px) * p.osw;
-        const bool last_row = orow == p.R - 1;
-        if (p.BN == 32) {
-          float v[32];
-          tmem_ld32(t_set + (uint32_t)(orow * 32), v);
-          if (last_row) {   // all of this warp's TMEM reads are done: hand the accumulator set back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
-          }
-          epilogue_store<2>(v, bias_s, nt * 32, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
-        } else {
-          float v[16];
-          tmem_ld16(t_set + (uint32_t)(orow * 16), v);
-          if (last_row) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
-          }
-          epilogue_store<1>(v, bias_s, nt * 16, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
+        const bool last_row = orow == R - 1;
+        float v[BN];
+        if (BN == 32) tmem_ld32(t_set + (uint32_t)(orow * BN), v);
+        else tmem_ld16(t_set + (uint32_t)(orow * BN), v);
+        if (last_row) {   // all of this warp's TMEM reads are done: hand the accumulator set back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
         }
+        epilogue_store<BN / 16>(v, bias_s, nt * BN, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
       }
       if (++acc == 2) {
         acc = 0;
@@ -444,8 +495,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -457,7 +507,8 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
   const int cout16 = round_up(L.Cout, 16);
   R.BN = cout16 == 16 ? 16 : 32;
   R.n_tiles = ceil_div(cout16, R.BN);
-  R.KB = g_tc_debug[2] == 64 ? 64 : 32;   // channel-chunk width: 32 (SW64, deep row pipeline) unless forced to 64
+  if (R.n_tiles * R.BN > 256) return true;   // bias staging area of the kernel
+  R.KB = (int)kKB;
   R.CinPadR = round_up(L.CinPad, R.KB);
   R.chunks = R.CinPadR / R.KB;
   // B[plane][nt*3*BN + (2-kh)*BN + co][kw*CinPadR + ci]: the three kh taps stacked along the MMA N dimension
@@ -509,8 +560,7 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
   cuuint32_t box[3] = {(cuuint32_t)R.KB, (cuuint32_t)(3 * R.BN), 2};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = tc_encode_fn()(&R.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dw, dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              R.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     err = "cuTensorMapEncodeTiled(row-kernel weights) failed for " + L.name + " code " + std::to_string((int)r);
@@ -530,13 +580,13 @@ bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, 
 }
 
 // up_src != nullptr: the first up_src->C channels of `in` are NOT read; they are produced inside the kernel as the
-// bilinear x2 upsample of *up_src (half resolution).  Needs 32-channel chunks and up_src->C % 32 == 0.
+// bilinear x2 upsample of *up_src (half resolution).  Needs up_src->C % 32 == 0.
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err, const ActView* up_src) {
   TcRowsPlan& R = tc.rows;
-  if (up_src && (R.KB != 32 || up_src->C % 32 || up_src->H * 2 != in.H || up_src->W * 2 != in.W ||
-                 up_src->sw % 8 || up_src->C > R.CinPadR)) {
-    err = "tc_rows_launch: fused upsample needs 32-channel chunks and a half-resolution source of 32k channels";
+  if (up_src && (up_src->C % 32 || up_src->H * 2 != in.H || up_src->W * 2 != in.W || up_src->sw % 8 ||
+                 up_src->C > R.CinPadR)) {
+    err = "tc_rows_launch: fused upsample needs a half-resolution source of 32k channels";
     return cudaErrorInvalidValue;
   }
   ViewKey key = std::make_tuple((const void*)in.hi, (const void*)in.lo, in.N, in.H, in.W, in.C);
@@ -553,8 +603,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
     cuuint32_t box[5] = {(cuuint32_t)R.KB, (cuuint32_t)kRowPx, 1, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = tc_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in.hi, dims, strides, box, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                R.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       err = "cuTensorMapEncodeTiled(row-kernel activations) failed for " + L.name + " code " + std::to_string((int)r);
@@ -564,34 +613,22 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   }
   RowsParams p;
   p.N = out.N; p.H = out.H; p.W = out.W;
-  p.R = kMaxR;
-  p.tiles_w = out.W / 128; p.tiles_h = out.H / p.R; p.n_tiles = R.n_tiles;
+  p.tiles_w = out.W / 128; p.tiles_h = out.H / kMaxR; p.n_tiles = R.n_tiles;
   p.total_tiles = p.tiles_w * p.tiles_h * out.N * R.n_tiles;
-  p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.BN = R.BN; p.Cout = L.Cout; p.act = L.act;
-  p.KB = R.KB; p.ksteps = R.KB / 16;
-  p.a_plane = round_up(kRowPx * R.KB * 2, 1024);
-  p.a_slot = 2 * p.a_plane;
-  p.sbo = 8 * R.KB * 2;
-  p.layout = R.KB == 64 ? 2 : 4;
-  p.b_kw_bytes = 2 * 3 * R.BN * R.KB * 2;
-  p.b_buf_bytes = 3 * p.b_kw_bytes;
-  p.idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+  p.chunks = R.chunks; p.CinPadR = R.CinPadR; p.Cout = L.Cout; p.act = L.act;
   p.out_hi = out.hi; p.out_lo = out.lo;
   p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
   p.bias = R.bias;
-  p.tmem_cols = 2 * p.R * R.BN;   // 512 (BN=32) or 256 (BN=16): powers of two
-  p.up_chunks = 0; p.xH = p.xW = p.xC = 0; p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
+  p.up_chunks = 0; p.xH = p.xW = 0;
   p.up_sh = p.up_sw = 0.f;
   p.a_c_off = 0;
-  p.kmask = g_tc_debug[6] == 1 ? R.kmask : ~0ull;   // VR_KSKIP=1: skip all-zero-weight channel groups (opt-in)
+  p.kmask = g_tc_debug[6] == 1 ? R.kmask : ~0ull;   // VR_KSKIP=0 issues the all-zero-weight channel groups too
   if (up_src) {
     // `in` is either the whole concat buffer (its first up_src->C channels are then never read) or only the skip
     // tensor, which starts at reduction index up_src->C
     if (in.C + up_src->C <= R.CinPadR) p.a_c_off = -up_src->C;
     p.up_chunks = up_src->C / 32;
-    p.xH = up_src->H; p.xW = up_src->W; p.xC = up_src->C;
-    p.x_hi = up_src->hi; p.x_lo = up_src->lo;
-    p.xsn = up_src->sn; p.xsh = up_src->sh; p.xsw = up_src->sw;
+    p.xH = up_src->H; p.xW = up_src->W;
     p.up_sh = in.H > 1 ? (float)(up_src->H - 1) / (float)(in.H - 1) : 0.f;   // as launch_upsample2x
     p.up_sw = in.W > 1 ? (float)(up_src->W - 1) / (float)(in.W - 1) : 0.f;
   }
@@ -616,19 +653,14 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
       return cudaErrorInvalidValue;
     }
   }
-  static bool attr_set = false;
-  static int num_sms = 0, max_smem = 0;
-  if (!attr_set) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 3072);
-    cudaFuncSetAttribute(conv_tc_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    attr_set = true;
+  const TcDevice& dv = tc_device();
+  if (!dv.ok) {
+    err = "tc_rows_launch: cannot query the current device";
+    return cudaErrorInvalidValue;
   }
+  const int b_bytes = R.BN == 16 ? (int)(2 * RowsGeom<16>::kBBuf) : (int)(2 * RowsGeom<32>::kBBuf);
   const int stage_bytes = p.up_chunks > 0 ? kStages * kStageBytes + kSrcPx * 128 : 0;
-  p.n_aslots = (max_smem - 3072 - 1024 - 2 * p.b_buf_bytes - stage_bytes) / p.a_slot;
+  p.n_aslots = (dv.max_smem - 3072 - 1024 - b_bytes - stage_bytes) / (int)kASlot;
   if (p.n_aslots > kMaxASlots) p.n_aslots = kMaxASlots;
   if (p.n_aslots < 2) {
     err = "tc_rows_launch: shared memory too small";
@@ -636,24 +668,21 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   }
   p.n_uslots = p.up_chunks > 0 ? p.n_aslots / 2 : 0;
   if (p.up_chunks > 0 && g_tc_debug[4] >= 1 && g_tc_debug[4] <= p.n_aslots - 2) p.n_uslots = g_tc_debug[4];
-  const int dyn = p.n_aslots * p.a_slot + 2 * p.b_buf_bytes + stage_bytes + 1024;
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;   // persistent: one CTA per SM
-  p.pdl = g_tc_debug[7] == 1 ? 1 : 0;   // VR_PDL=1 (opt-in)
-  if (p.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)kRowsThreads);
-    cfg.dynamicSmemBytes = (size_t)dyn;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_tc_rows_kernel, it->second, R.map_b, up_src ? map_x : it->second, p);
-  }
-  conv_tc_rows_kernel<<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
+  const int dyn = p.n_aslots * (int)kASlot + b_bytes + stage_bytes + 1024;
+  const int grid = p.total_tiles < dv.num_sms ? p.total_tiles : dv.num_sms;   // persistent: one CTA per SM
+  if (R.BN == 16)
+    conv_tc_rows_kernel<16><<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
+  else
+    conv_tc_rows_kernel<32><<<grid, kRowsThreads, dyn, s>>>(it->second, R.map_b, up_src ? map_x : it->second, p);
   return cudaGetLastError();
+}
+
+// cudaFuncSetAttribute is per device: called by tc_device() the first time a device is used (conv_tc.cu)
+void tc_rows_set_attributes(int max_smem) {
+  cudaFuncSetAttribute(conv_tc_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 3072);
+  cudaFuncSetAttribute(conv_tc_rows_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(conv_tc_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 3072);
+  cudaFuncSetAttribute(conv_tc_rows_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
 }  // namespace vr

@@ -203,7 +203,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   // slice is never materialised: cat1 then holds ONLY the skip tensor e1, dense, so that the row kernel's TMA reads of
   // it are contiguous (inside the wide concat buffer e1 was a 32..64-byte island per 160..256-byte pixel and the
   // 256-byte L2 promotion over-fetched: 292 MB of DRAM reads for 134 MB of operands on stg1_low.dec1).
-  P.skip_only = cfg_.conv_mode == 0 && g_tc_debug[5] == 1 && g_tc_debug[1] == 0 && g_tc_debug[2] != 64 &&
+  P.skip_only = cfg_.conv_mode == 0 && g_tc_debug[5] == 1 && g_tc_debug[1] == 0 &&
                 (2 * n) % 32 == 0 && W % 128 == 0 && H % 8 == 0;
   const int lg = P.skip_only ? 32 : 16;
   const int c1 = round_up(3 * n + lg, 16);
@@ -212,16 +212,12 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.cat1 = make_buffer(Nb, H, W, P.skip_only ? round_up(n, 16) : c1);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
-  // Feature maps that feed a 3x3 stride-1 convolution at W <= 64 carry zero pad pixels after every row (>= the
-  // horizontal dilation of their consumers: 1, or 6 for the ASPP input) so that the flat-halo kernel can read the
-  // taps as shifted views of one contiguous pixel segment.
-  const int pw = (g_tc_debug[3] == 1 && W / 4 <= 64) ? 2 : 0;   // only when the (experimental) flat kernel is enabled
-  P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n, pw);
-  P.cat3 = make_buffer(Nb, H / 4, W / 4, 10 * n, pw);
-  P.t4 = make_buffer(Nb, H / 8, W / 8, 6 * n, pw);
-  P.cat4 = make_buffer(Nb, H / 8, W / 8, 14 * n, pw);
-  P.t5 = make_buffer(Nb, H / 16, W / 16, 8 * n, pw);
-  P.e5 = make_buffer(Nb, H / 16, W / 16, 8 * n, pw ? 6 : 0);
+  P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
+  P.cat3 = make_buffer(Nb, H / 4, W / 4, 10 * n);
+  P.t4 = make_buffer(Nb, H / 8, W / 8, 6 * n);
+  P.cat4 = make_buffer(Nb, H / 8, W / 8, 14 * n);
+  P.t5 = make_buffer(Nb, H / 16, W / 16, 8 * n);
+  P.e5 = make_buffer(Nb, H / 16, W / 16, 8 * n);
   P.pool = make_buffer(Nb, 1, W / 16, 8 * n);
   P.f1 = make_buffer(Nb, 1, W / 16, 8 * n);
   P.acat = make_buffer(Nb, H / 16, W / 16, 40 * n);
@@ -839,7 +835,7 @@ bool Engine::debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   std::vector<void*> tmp;
   std::swap(tmp, allocs_);
-  Buffer bin = make_buffer(N, H, W, cin_pad, (g_tc_debug[3] == 1 && W <= 64) ? (dil_w > 2 ? dil_w : 2) : 0);
+  Buffer bin = make_buffer(N, H, W, cin_pad);
   Buffer bout = make_buffer(N, Ho, Wo, round_up(Cout, 8));
   ConvLayer L;
   L.name = "debug_conv";

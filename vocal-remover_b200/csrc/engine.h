@@ -23,8 +23,7 @@ struct Buffer {   // a whole NHWC split-bf16 allocation
   bf16* hi = nullptr;
   bf16* lo = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
-  int Wp = 0;   // row pitch in pixels (>= W): the Wp - W trailing pixels of every row are permanent zeros, which
-                // is the horizontal conv padding of the flat-halo tensor-core kernel (conv_tc_flat.cu)
+  int Wp = 0;   // row pitch in pixels (>= W): the Wp - W trailing pixels of every row are permanent zeros
   ActView view(int n, int h0, int h, int c0, int c) const {
     ActView v;
     const int64_t off = (int64_t)h0 * Wp * C + c0;

@@ -21,12 +21,6 @@ struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 1
   std::map<ViewKey, CUtensorMap> map_a;
 };
 
-struct TcFlatPlan {   // flat-halo variant: 3x3, stride 1, W <= 64 with zero pad pixels after every row (conv_tc_flat.cu)
-  bool ok = false;
-  CUtensorMap map_b;
-  std::map<ViewKey, CUtensorMap> map_a;
-};
-
 struct TcConv {
   int CinPadTC = 0, KB = 0, cchunks = 0, SUBS = 0, taps = 0, Ktot = 0, CoutPadN = 0, BN = 0, n_tiles = 0;
   bf16* w_planes = nullptr;   // [2][CoutPadN][Ktot]
@@ -34,7 +28,6 @@ struct TcConv {
   CUtensorMap map_b;
   std::map<ViewKey, CUtensorMap> map_a;
   TcRowsPlan rows;
-  TcFlatPlan flat;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -49,11 +42,20 @@ bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<voi
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
                            std::string& err, const ActView* up_src = nullptr);
-// conv_tc_flat.cu
-bool tc_flat_prepare(ConvLayer& L, TcConv& tc, std::string& err);
-bool tc_flat_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
-cudaError_t tc_flat_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
-                           std::string& err);
-extern int g_tc_debug[8];   // [0] unused, [1] disable the row kernel, [2] = 64: 64-channel chunks, [3] = 1 enables the experimental flat-halo kernel, [4] = k: k of the row slots feed the interpolation warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1: the row kernel skips channel groups whose weights are all zero, [7] = 1: tensor-core convolutions are launched with programmatic stream serialization (prologue overlaps the previous kernel's tail)
+void tc_rows_set_attributes(int max_smem);
+
+// Properties of the CURRENT device, cached per device ordinal.  The first use on a device also opts the tensor-core
+// kernels in to their dynamic shared memory there (cudaFuncSetAttribute is per device, so a process that drives
+// several GPUs - one context per GPU - must do it on each of them).
+struct TcDevice {
+  bool ok = false;
+  int num_sms = 0, max_smem = 0;
+};
+const TcDevice& tc_device();
+
+// validation knobs (vr_debug_set): [1] = 1 disables the row kernel, [4] = k: k of the row slots feed the interpolation
+// warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1 (default): the row
+// kernel skips channel groups whose weights are all zero; the other entries are unused
+extern int g_tc_debug[8];
 
 }  // namespace vr

@@ -75,14 +75,8 @@ def load_library():
         fn.restype = res
         fn.argtypes = args
     # validation knobs of the tensor-core kernels (see vr_debug_set in include/vr_b200.h)
-    if os.environ.get('VR_ROWS_KB'):
-        lib.vr_debug_set(2, int(os.environ['VR_ROWS_KB']))
-    if os.environ.get('VR_FLAT'):
-        lib.vr_debug_set(3, int(os.environ['VR_FLAT']))
     if os.environ.get('VR_FUSE_UP'):
         lib.vr_debug_set(5, int(os.environ['VR_FUSE_UP']))
-    if os.environ.get('VR_PDL'):
-        lib.vr_debug_set(7, int(os.environ['VR_PDL']))
     if os.environ.get('VR_KSKIP'):
         lib.vr_debug_set(6, int(os.environ['VR_KSKIP']))
     if os.environ.get('VR_USLOTS'):
