@@ -12,6 +12,12 @@ one mask gather to rank 0 before the overlap-add).  Prints ONE JSON line (rank 0
   e2e        same through the public host-buffer call (pinned host wave -> pinned host stems), copies inside
   roofline   tcgen05 convolution kernel: algorithmic conv FLOPs / CUDA-event kernel time vs measured bf16 peak
   cpu_baseline  the CPU oracle port of the reference path (oracle/), all host threads, bounded sample
+  parity     measured max-abs errors of this build on the 10 s golden fixture (tests/golden), before timing
+  tta        the same track with --tta (BASELINE configs[3], 163 windows)
+  strong_2400s  a fixed 40-minute stream (BASELINE configs[4], 808 windows) on the N GPUs of the run
+  cudnn_baseline  the reference's own GPU arithmetic: the oracle's functional restatement of the reference modules on
+             cuda:0 through stock PyTorch / cuDNN (TF32 convolutions allowed, the torch default) + torch.stft/istft
+  mgpu_check (N > 1) sharded vs single-GPU stems on a 31 s track, with and without --tta; the run fails above 1e-5
 --impl reference runs only that CPU arm (the reference itself is Python over librosa and cannot travel to the
 GPU box; oracle/ is its restatement, validated against the unmodified reference in tests/).
 """
@@ -40,6 +46,7 @@ CONV_FLOP_PER_WINDOW = 135.714e9
 # passes, / 44 (ncu capture profiles/r01_launches_bench30s_fused.csv, decoder upsample fused into dec1/dec2; the build
 # before that fusion moved 1.225 GB); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
 CONV_DRAM_BYTES_PER_WINDOW = 0.879e9
+GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'ref_10s_default.npz')
 
 
 def measured_peaks():
@@ -183,6 +190,96 @@ def write_layer_table(ctx, path):
                                                                       gf / ms if ms > 0 else 0.0))
 
 
+def parity_block(sp, dev):
+    """Measured errors of THIS build against the golden tensors the unmodified reference produced for the 10 s input
+    (tests/golden/ref_10s_default.npz, oracle/make_golden.py): mask, --tta mask, masked spectrogram in normalised units."""
+    import inference
+    from lib import spec_utils, synth
+    if not os.path.exists(GOLDEN):
+        return None
+    g = np.load(GOLDEN)
+    wave = synth.sine_mix(10.0)
+    X = spec_utils.wave_to_spectrogram(wave, 1024, 2048)
+    d_spec = torch.from_numpy(X).to(dev)
+    m = sp._mask_device(d_spec, False).cpu().numpy()
+    mt = sp._mask_device(d_spec, True).cpu().numpy()
+    y, v = sp.separate(X)
+    absmax = float(g['absmax'])
+    return {
+        'input': '10 s synthetic sine mix, 4 windows (BASELINE configs[1]); golden = unmodified reference on CPU fp32',
+        'gate': 1e-3,
+        'mask_max_abs_vs_golden_10s': float(np.abs(m[:, ::8, :] - g['mask_sub']).max()),
+        'tta_mask_max_abs_vs_golden_10s': float(np.abs(mt[:, ::8, :] - g['mask_tta_sub']).max()),
+        'y_spec_max_abs_over_absmax_vs_golden_10s': float(np.abs(y[:, ::16, :] - g['y_sub']).max() / absmax),
+        'parity_unpinned': ['stft', 'istft'],
+        'parity_unpinned_note': 'librosa (the reference\'s STFT/iSTFT) is absent offline; the restatement is cross-checked '
+                                'against torch.stft and scipy.signal (tests/test_oracle_stft.py), not against librosa',
+    }
+
+
+def cudnn_baseline_arm(dev, wave, batch, steps=2):
+    """The reference's GPU path (inference.py:124-132 with --gpu 0) restated with stock PyTorch on cuda:0: torch.stft,
+    the oracle's functional CascadedNet (F.conv2d -> cuDNN with TF32 allowed, nn.LSTM's fused kernel), mask multiply,
+    torch.istft; windows batched like the product arm.  A baseline leg (like cpu_baseline), never the product path."""
+    from lib import synth
+    from oracle import net_oracle
+    sd = net_oracle.to_device(synth.to_torch_state_dict(synth.make_state_dict()), dev)
+    tf32 = bool(torch.backends.cudnn.allow_tf32)
+    w = torch.from_numpy(wave).to(dev)
+    win = torch.hann_window(2048, periodic=True, device=dev)
+    roi, off, crop = 128, 64, 256
+
+    def one():
+        X = torch.stft(w, 2048, 1024, window=win, center=True, pad_mode='constant', return_complex=True)   # (2, 1025, T)
+        T = X.shape[2]
+        pad_r = roi - (T % roi) + off
+        Xp = torch.nn.functional.pad(X, (off, pad_r))
+        mag = Xp.abs() / X.abs().max()
+        n = (Xp.shape[2] - 2 * off) // roi
+        masks = []
+        for i in range(0, n, batch):
+            xb = torch.stack([mag[:, :, j * roi:j * roi + crop] for j in range(i, min(n, i + batch))])
+            mb = net_oracle.predict_mask(sd, xb, 2048, off)
+            masks.append(torch.cat(list(mb), dim=2))
+        mask = torch.cat(masks, dim=2)[:, :, :T]
+        y, v = X * mask, X * (1 - mask)
+        return (torch.istft(y, 2048, 1024, window=win, center=True), torch.istft(v, 2048, 1024, window=win, center=True))
+
+    with torch.no_grad():
+        one()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            one()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1) / steps
+    secs = wave.shape[1] / SR
+    del sd
+    torch.cuda.empty_cache()
+    return {'value': secs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps, 'window_batch': batch,
+            'tf32_convolutions': tf32,
+            'what': 'torch.stft -> functional CascadedNet on cuDNN (oracle/net_oracle on cuda:0, fused nn.LSTM kernel) -> '
+                    'mask -> torch.istft x2 on the same %d s track, device-resident, CUDA-event timed' % int(secs)}
+
+
+def mgpu_check(sp, dev, world, rank):
+    """Sharded vs single-GPU stems on a 31 s track (every rank computes the single-GPU reference itself), with and
+    without --tta.  Returns the max abs differences on rank 0."""
+    from lib import synth
+    from lib import distributed as vr_dist
+    wave = torch.from_numpy(synth.sine_mix(31.0)).to(dev)
+    out = {}
+    for tta, key in ((False, 'max_diff'), (True, 'tta_max_diff')):
+        ref_inst, ref_voc = sp.separate_wave(wave, tta=tta)
+        for _ in range(2):   # twice: cached buffers / barriers must be reusable
+            inst, voc = vr_dist.separate_wave(sp, wave, tta=tta, world=world, rank=rank)
+        if rank == 0:
+            out[key] = max((inst - ref_inst).abs().max().item(), (voc - ref_voc).abs().max().item())
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import inference
@@ -218,32 +315,74 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, per_step=None):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks.  per_step
+        (a list) additionally receives every step's own duration (events between steps cost nothing measurable)."""
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             fn()
-        ev1.record()
+            evs[i + 1].record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
+        ms = evs[0].elapsed_time(evs[steps])
+        each = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms] + each, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+            ms, each = t[0].item(), t[1:].tolist()
+        if per_step is not None:
+            per_step.extend(each)
         return ms
+
+    # measured errors of this build on the 10 s golden fixture, before any timing (single-GPU path of this rank)
+    parity = parity_block(sp, dev) if rank == 0 else None
+    check = None
+    if world > 1:
+        check = mgpu_check(sp, dev, world, rank)
 
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ctx.launch_count()
-    ms = timed(step_device, args.steps)
+    per_step = []
+    ms = timed(step_device, args.steps, per_step)
     launches = ctx.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms_step = ms / args.steps
     value = seconds / (ms_step * 1e-3)
+    ms_median = sorted(per_step)[len(per_step) // 2]
+
+    # ---- BASELINE configs[3]: the same track with --tta (second, half-window-shifted pass; inference.py:83-102) ----
+    def step_tta():
+        return vr_dist.separate_wave(sp, d_wave, tta=True, world=world, rank=rank)
+
+    tta_steps = max(1, min(args.steps, 3))
+    step_tta()
+    tta_ms = timed(step_tta, tta_steps) / tta_steps
+
+    # ---- BASELINE configs[4]: a fixed 40-minute stream on the N GPUs of this run (strong scaling) ----
+    strong = None
+    if not args.no_strong and args.seconds_per_gpu >= SECONDS_PER_GPU:
+        reps = int(round(2400.0 / SECONDS_PER_GPU))
+        base = d_wave[:, :int(SECONDS_PER_GPU * SR)]
+        d_long = base.repeat(1, reps).contiguous()
+        Tl = 1 + d_long.shape[1] // 1024
+
+        def step_long():
+            return vr_dist.separate_wave(sp, d_long, tta=False, world=world, rank=rank)
+
+        step_long()
+        long_steps = 2
+        long_ms = timed(step_long, long_steps) / long_steps
+        strong = {'value': 2400.0 / (long_ms * 1e-3), 'unit': UNIT, 'ms_per_step': long_ms, 'steps': long_steps,
+                  'seconds_of_audio': 2400, 'windows': (Tl + (128 - Tl % 128)) // 128, 'n_gpus': world,
+                  'note': 'the first 240 s of the synthetic track repeated 10 times; the same stream at every N, so '
+                          'value(N) / value(1) is the strong-scaling speed-up'}
+        del d_long
+        torch.cuda.empty_cache()
 
     # ---- roofline pass: one more step of the same workload with a CUDA event pair around every convolution
     # launch (recorded inside the library on the launching stream); the two band streams are serialised while
@@ -283,7 +422,7 @@ def run_gpu(args):
     roof = None
     if tc_n > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
-        roof = {'bound': 'tensor', 'kernel': 'conv_tc_rows_kernel + conv_tc_flat_kernel + conv_tc_kernel (tcgen05 implicit-GEMM conv family, '
+        roof = {'bound': 'tensor', 'kernel': 'conv_tc_rows_kernel + conv_tc_kernel (tcgen05 implicit-GEMM conv family, '
                           'bf16x3 split precision)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                 'traffic': CONV_DRAM_BYTES_PER_WINDOW * n_windows / world / max(1.0, tc_n),
@@ -297,14 +436,27 @@ def run_gpu(args):
                 'cuda_core_conv': {'ms': cc_ms, 'launches': int(cc_n),
                                    'tflops': (cc_flops / (cc_ms * 1e-3) / 1e12) if cc_ms > 0 else None}}
     line = None
+    if check is not None:
+        flag = torch.tensor([1.0 if (rank == 0 and any(not (v <= 1e-5) for v in check.values())) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() > 0:   # every rank leaves together
+            if rank == 0:
+                print(json.dumps({'error': 'multi-GPU check failed (sharded stems differ from the single-GPU stems)',
+                                  'mgpu_check': check}))
+            dist.destroy_process_group()
+            sys.exit(3)
     if rank == 0:
+        cudnn = None
+        if not (args.no_cudnn_baseline or world > 1):   # like the CPU arm: reported at N=1 only
+            cudnn = cudnn_baseline_arm(dev, wave, args.batch)
         if args.no_cpu_baseline or world > 1:   # the CPU arm is reported at N=1 only
             cpu_val, cores, secs = None, 0, 0.0
         else:
             cpu_val, cpu_dt, cores, secs = cpu_reference_arm(1, 1, 12.0)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_step, 'ms_per_step_median': ms_median, 'value_at_median': seconds / (ms_median * 1e-3),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16x3 (split-bf16 operands hi+lo, 3 tcgen05 passes, fp32 accumulate); fft/lstm fp32',
             'data': 'synthetic',
             'config': {'workload': workload_text(seconds, n_windows, args.batch),
@@ -319,6 +471,12 @@ def run_gpu(args):
                     'note': 'bytes are totals over all ranks; with N > 1 every rank moves only its own slice of the '
                             'wave / stems over its own PCIe link (lib/distributed.py, sharded mode)'},
             'gpu_launches': int(launches),
+            'parity': parity,
+            'mgpu_check': check,
+            'tta': {'value': seconds / (tta_ms * 1e-3), 'unit': UNIT, 'ms_per_step': tta_ms, 'steps': tta_steps,
+                    'windows': 2 * n_windows + 1, 'config': 'BASELINE configs[3]: the same track with --tta'},
+            'strong_2400s': strong,
+            'cudnn_baseline': cudnn,
             'roofline': roof,
             'cpu_baseline': {'value': cpu_val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': 'first %.0f s of the same track through the CPU oracle port (oracle/), 1 step '
@@ -341,6 +499,8 @@ def main():
     ap.add_argument('--layers', type=str, default='', help='write the per-layer conv timing table of the profiled '
                                                            'step to this file')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU arm (profiling runs only)')
+    ap.add_argument('--no-cudnn-baseline', action='store_true', help='skip the stock-PyTorch / cuDNN GPU arm')
+    ap.add_argument('--no-strong', action='store_true', help='skip the 40-minute strong-scaling sub-record')
     ap.add_argument('--seconds-per-gpu', type=float, default=SECONDS_PER_GPU,
                     help='track length per GPU (default 240 s = BASELINE configs[2]; shorter only for profiling)')
     args = ap.parse_args()

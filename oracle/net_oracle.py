@@ -28,6 +28,13 @@ def _t(sd, key):
     return v
 
 
+def to_device(sd, device):
+    """Copy of the state_dict on ``device`` (float tensors only are moved; used by the cuDNN baseline leg of bench.py,
+    which runs this same functional restatement on cuda:0 with PyTorch's default TF32 convolutions)."""
+    return {k: (v if not torch.is_tensor(v) else v.to(device)) for k, v in
+            ((k, _t(sd, k)) for k in sd)}
+
+
 def conv_bn_act(sd, p, x, stride=1, pad=1, dil=1, act='relu'):
     """lib/layers.py:8-26 at state_dict prefix ``p``."""
     w = _t(sd, p + '.conv.0.weight')
@@ -84,6 +91,17 @@ def lstm_module(sd, p, x):
     h = conv_bn_act(sd, p + '.conv', x, pad=0)[:, 0]          # N, nbins, nframes
     h = h.permute(2, 0, 1).contiguous()                       # nframes, N, nbins
     hid = _t(sd, p + '.lstm.weight_hh_l0').shape[1]
+    if x.is_cuda:
+        # the reference module is nn.LSTM (cuDNN on a GPU): same fused call, not a Python time loop
+        flat = [_t(sd, f'{p}.lstm.{n}_l0{sfx}') for sfx in ('', '_reverse')
+                for n in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')]
+        zeros = torch.zeros(2, N, hid, device=x.device, dtype=x.dtype)
+        out, _, _ = torch._VF.lstm(h, (zeros, zeros), flat, True, 1, 0.0, False, True, False)
+        h2 = out.reshape(nframes * N, 2 * hid)
+        h2 = F.linear(h2, _t(sd, p + '.dense.0.weight'), _t(sd, p + '.dense.0.bias'))
+        h2 = F.batch_norm(h2, _t(sd, p + '.dense.1.running_mean'), _t(sd, p + '.dense.1.running_var'),
+                          _t(sd, p + '.dense.1.weight'), _t(sd, p + '.dense.1.bias'), False, 0.0, BN_EPS)
+        return F.relu(h2).reshape(nframes, N, 1, nbins).permute(1, 2, 3, 0)
     outs = []
     for sfx, rev in (('', False), ('_reverse', True)):
         w_ih = _t(sd, f'{p}.lstm.weight_ih_l0{sfx}')

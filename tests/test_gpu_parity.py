@@ -10,7 +10,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import checksum
+from conftest import checksum, record_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -44,6 +44,7 @@ def test_stft_matches_oracle_and_golden(wave10, golden_default):
     R = stft_oracle.wave_to_spectrogram(wave10, 1024, 2048)
     assert S.shape == R.shape and S.dtype == np.complex64
     scale = np.abs(R).max()
+    record_parity('stft_10s_relative_vs_oracle', np.abs(S - R).max() / scale, 5e-6)
     assert np.abs(S - R).max() / scale < 5e-6
     assert np.abs(S[:, ::16, :] - golden_default['X_sub']).max() / scale < 5e-6
 
@@ -55,6 +56,7 @@ def test_istft_matches_oracle_and_roundtrip(wave10):
     w = spec_utils.spectrogram_to_wave(R, 1024)
     wr = stft_oracle.spectrogram_to_wave(R, 1024)
     assert w.shape == wr.shape and w.dtype == np.float32
+    record_parity('istft_10s_vs_oracle', np.abs(w - wr).max(), 5e-6)
     assert np.abs(w - wr).max() < 5e-6
     assert np.abs(w - wave10[:, :w.shape[1]]).max() < 5e-6
     w0 = spec_utils.spectrogram_to_wave(R[0], 1024)   # 2-D mono input (lib/spec_utils.py:158-159)
@@ -145,6 +147,7 @@ def test_predict_mask_and_forward_vs_oracle(default_model, wave10):
     ref = net_oracle.forward(sd, torch.from_numpy(x))
     got = default_model.forward(torch.from_numpy(x).cuda()).cpu()
     assert got.shape == ref.shape == (2, 2, 1025, 256)
+    record_parity('forward_2windows_mask_vs_oracle', (got - ref).abs().max().item(), MASK_TOL)
     assert (got - ref).abs().max().item() < MASK_TOL
     got_c = default_model.predict_mask(torch.from_numpy(x).cuda()).cpu()
     assert got_c.shape == (2, 2, 1025, 128)
@@ -169,6 +172,7 @@ def test_separate_10s_vs_reference_golden(default_model, wave10, golden_default)
     big = np.abs(X) > 1e-2 * absmax
     mask = np.real(y * np.conj(X)) / np.maximum(np.abs(X) ** 2, 1e-20)
     err = np.abs(mask[:, ::8, :] - g['mask_sub'])[big[:, ::8, :]].max()
+    record_parity('separate_10s_y_spec_normalised_vs_reference_golden', np.abs(y[:, ::16, :] - g['y_sub']).max() / absmax, MASK_TOL)
     assert err < MASK_TOL
     assert np.abs(y + v - X).max() / absmax < 1e-6
     cs = checksum(y)
@@ -188,9 +192,11 @@ def test_mask_10s_direct_and_tta_vs_golden(default_model, wave10, golden_default
     sp = inference.Separator(default_model, _dev(), 3, 256, False)   # batch 3: 4 windows -> ragged last batch
     d_spec = torch.from_numpy(X).cuda()
     m = sp._mask_device(d_spec, False).cpu().numpy()
+    record_parity('mask_10s_vs_reference_golden', np.abs(m[:, ::8, :] - g['mask_sub']).max(), MASK_TOL)
     assert np.abs(m[:, ::8, :] - g['mask_sub']).max() < MASK_TOL
     assert np.array_equal(m[:, 1024, :], m[:, 1023, :])           # replicate-padded Nyquist row (lib/nets.py:111-115)
     mt = sp._mask_device(d_spec, True).cpu().numpy()
+    record_parity('mask_10s_tta_vs_reference_golden', np.abs(mt[:, ::8, :] - g['mask_tta_sub']).max(), MASK_TOL)
     assert np.abs(mt[:, ::8, :] - g['mask_tta_sub']).max() < MASK_TOL
     # the TTA normaliser is |lexicographic complex max|
     ctx = sp._ctx()
@@ -219,6 +225,8 @@ def test_separate_wave_fused_matches_staged(default_model, wave10, golden_defaul
     sp = inference.Separator(default_model, _dev(), 4, 256, False)
     inst, voc = sp.separate_wave(wave10)
     assert inst.shape == (2, 440320) and voc.shape == inst.shape
+    record_parity('wave_10s_instruments_vs_reference_golden', np.abs(inst[:, ::16] - g['wave_inst_sub']).max(), 1e-3)
+    record_parity('wave_10s_vocals_vs_reference_golden', np.abs(voc[:, ::16] - g['wave_voc_sub']).max(), 1e-3)
     assert np.abs(inst[:, ::16] - g['wave_inst_sub']).max() < 1e-3
     assert np.abs(voc[:, ::16] - g['wave_voc_sub']).max() < 1e-3
     d_inst, d_voc = sp.separate_wave(torch.from_numpy(wave10).cuda())
@@ -237,6 +245,7 @@ def test_small_config_vs_reference_golden(golden_small):
     X = stft_oracle.wave_to_spectrogram(synth.sine_mix(3.0), 256, 512)
     sp = inference.Separator(m, _dev(), 2, 192, False)
     mask = sp._mask_device(torch.from_numpy(X).cuda(), False).cpu().numpy()
+    record_parity('mask_3s_small_config_vs_reference_golden', np.abs(mask[:, ::2, :] - golden_small['mask_sub']).max(), MASK_TOL)
     assert np.abs(mask[:, ::2, :] - golden_small['mask_sub']).max() < MASK_TOL
 
 
@@ -276,6 +285,7 @@ def test_edge_lengths_vs_oracle(default_model, n_frames):
     sp = inference.Separator(default_model, _dev(), 4, 256, False)
     got = sp._mask_device(torch.from_numpy(X).cuda(), False).cpu().numpy()
     assert got.shape == ref.shape == (2, 1025, n_frames)
+    record_parity('mask_edge_%d_frames_vs_oracle' % n_frames, np.abs(got - ref).max(), MASK_TOL)
     assert np.abs(got - ref).max() < MASK_TOL
     inst, voc = sp.separate_wave(wave)
     assert inst.shape == (2, 1024 * (n_frames - 1))
@@ -353,3 +363,22 @@ def test_zero_group_skipping_is_exact(default_model, wave10):
             assert torch.equal(base, switched)
     finally:
         lib.vr_debug_set(6, 1)
+
+
+def test_silent_track_does_not_poison_the_context(default_model, wave10, golden_default):
+    """A silent track has max|X| = 0: the normaliser guard packs zeros (finite mask) and, more importantly, nothing
+    non-finite may survive in the shared activation buffers - the next track on the same Separator must be unaffected."""
+    import inference
+    sp = inference.Separator(default_model, _dev(), 4, 256, False)
+    before, _ = sp.separate_wave(wave10)
+    silent = np.zeros((2, 44100 * 3), dtype=np.float32)
+    inst, voc = sp.separate_wave(silent)
+    assert np.isfinite(inst).all() and np.isfinite(voc).all()
+    assert np.abs(inst).max() == 0.0 and np.abs(voc).max() == 0.0
+    bad = silent.copy()
+    bad[0, 1000] = np.nan
+    bad[1, 5000] = np.inf
+    sp.separate_wave(bad)                       # whatever this returns, it must not leak into later calls
+    after, _ = sp.separate_wave(wave10)
+    assert np.isfinite(after).all()
+    assert np.array_equal(before, after)

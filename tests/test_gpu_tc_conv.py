@@ -3,6 +3,7 @@ layer class by layer class (3x3, strided, dilated, 1x1, ragged batch, multi-N-ti
 import pytest
 import torch
 
+from conftest import record_parity
 from test_gpu_parity import _ref_conv, _run_debug_conv
 
 pytestmark = pytest.mark.gpu
@@ -46,6 +47,7 @@ def test_conv_tcgen05_vs_torch(case):
     y = _run_debug_conv(ctx, x, w, b, k, stride, dil, act, 1)
     ref = _ref_conv(x, w, b, k, stride, dil, act)
     err = (y - ref).abs().max().item()
+    record_parity('conv_tcgen05_%s' % '_'.join(str(v) for v in case).replace(' ', ''), err / max(1.0, ref.abs().max().item()), 2e-4)
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), err
     # and the CUDA-core kernel agrees with it even more closely (same split-bf16 storage)
     y2 = _run_debug_conv(ctx, x, w, b, k, stride, dil, act, 0)

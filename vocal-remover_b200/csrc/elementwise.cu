@@ -23,13 +23,20 @@ __global__ void pack_mag_from_spec_kernel(const float2* __restrict__ spec, int b
   int bin = (int)(r % max_bin);
   int n = (int)(r / max_bin);
   int64_t t = (int64_t)(first_window + n) * roi + tw - pad_l;
-  float inv = 1.0f / *norm;
+  // A silent track has max|X| = 0 (the reference then divides 0/0 and writes NaN stems for that one file).  Here a
+  // NaN would outlive the call: stage-1/2 layers read the aux channel slots of the shared input buffer through zero
+  // weights, and 0 * NaN = NaN inside the MMA would poison every later track on this context.  So a zero / non-finite
+  // normaliser packs zeros, and non-finite magnitudes (NaN / Inf samples) are packed as zeros as well.
+  const float nv = *norm;
+  const float inv = (nv > 0.f && nv <= 3.0e38f) ? 1.0f / nv : 0.f;
   float m0 = 0.f, m1 = 0.f;
   if (t >= 0 && t < T) {
     float2 a = spec[((int64_t)0 * bins + bin) * T + t];
     float2 b = spec[((int64_t)1 * bins + bin) * T + t];
     m0 = hypotf(a.x, a.y) * inv;
     m1 = hypotf(b.x, b.y) * inv;
+    if (!(m0 <= 3.0e38f)) m0 = 0.f;   // also catches NaN
+    if (!(m1 <= 3.0e38f)) m1 = 0.f;
   }
   int64_t off = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)tw * dst.sw;
   bf16 h0, l0, h1, l1;
@@ -60,6 +67,8 @@ __global__ void pack_mag_from_float_kernel(const float* __restrict__ mag, int bi
   int n = (int)(r / max_bin);
   float m0 = mag[(((int64_t)n * 2 + 0) * bins + bin) * W + tw];
   float m1 = mag[(((int64_t)n * 2 + 1) * bins + bin) * W + tw];
+  if (!(fabsf(m0) <= 3.0e38f)) m0 = 0.f;   // non-finite inputs must not reach the shared activation buffers (see above)
+  if (!(fabsf(m1) <= 3.0e38f)) m1 = 0.f;
   int64_t off = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)tw * dst.sw;
   bf16 h0, l0, h1, l1;
   split_bf16(m0, h0, l0);

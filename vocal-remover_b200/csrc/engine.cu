@@ -424,9 +424,26 @@ void Engine::profile_enable(bool on) {
   profiling_ = on;
 }
 
+int Engine::prof_begin(const std::string& name, int kind, double flops, int N, int H, int W, cudaStream_t s) {
+  if (!profiling_) return -1;
+  ProfRec rec;
+  cudaEventCreate(&rec.a);
+  cudaEventCreate(&rec.b);
+  rec.tc = kind; rec.flops = flops; rec.name = name;
+  rec.N = N; rec.H = H; rec.W = W;
+  cudaEventRecord(rec.a, s);
+  prof_.push_back(rec);
+  return (int)prof_.size() - 1;
+}
+
+void Engine::prof_end(int idx, cudaStream_t s) {
+  if (idx >= 0) cudaEventRecord(prof_[(size_t)idx].b, s);
+}
+
 bool Engine::profile_read(double* out6) {
   for (int i = 0; i < 6; ++i) out6[i] = 0.0;
   for (auto& r : prof_) {
+    if (r.tc > 1) continue;   // only the convolutions enter the roofline sums
     if (!ck(cudaEventSynchronize(r.b), "profile sync")) return false;
     float ms = 0.f;
     if (!ck(cudaEventElapsedTime(&ms, r.a, r.b), "profile elapsed")) return false;
@@ -455,22 +472,11 @@ bool Engine::profile_dump(std::string& text) {
 bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src) {
   ++launches;
   const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
-  ProfRec rec;
-  if (profiling_) {
-    cudaEventCreate(&rec.a);
-    cudaEventCreate(&rec.b);
-    rec.tc = use_tc ? 1 : 0;
-    // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
-    rec.flops = 2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k;
-    rec.name = up_src ? L.name + "+up" : L.name;
-    rec.N = out.N; rec.H = out.H; rec.W = out.W;
-    cudaEventRecord(rec.a, s);
-  }
+  // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
+  const int pi = prof_begin(up_src ? L.name + "+up" : L.name, use_tc ? 1 : 0,
+                            2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k, out.N, out.H, out.W, s);
   bool ok = run_conv_inner(L, in, out, use_tc, s, up_src);
-  if (profiling_) {
-    cudaEventRecord(rec.b, s);
-    prof_.push_back(rec);
-  }
+  prof_end(pi, s);
   return ok;
 }
 
@@ -503,7 +509,8 @@ bool Engine::run_decoder(ConvLayer& L, const ActView& low, const Buffer& cat, in
     return false;
   }
   ++launches;
-  if (!ck(launch_upsample2x(low, cat.view(N, 0, cat.H, 0, low.C), s), "decoder upsample")) return false;
+  if (!timed("upsample2x", N, cat.H, cat.W, s, [&] { return ck(launch_upsample2x(low, cat.view(N, 0, cat.H, 0, low.C), s), "decoder upsample"); }))
+    return false;
   return run_conv(L, cat_all, out, s);
 }
 
@@ -523,18 +530,22 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
   // ASPP (lib/layers.py:92-105)
   const int c8 = 8 * n, h16 = H / 16;
   launches += 2;
-  if (!ck(launch_pool_freq_mean(P.e5.all(N), P.pool.all(N), s), "aspp pool")) return false;
+  if (!timed("aspp.pool_freq_mean", N, h16, P.W / 16, s, [&] { return ck(launch_pool_freq_mean(P.e5.all(N), P.pool.all(N), s), "aspp pool"); }))
+    return false;
   if (!run_conv(P.aspp1, P.pool.all(N), P.f1.all(N), s)) return false;
-  if (!ck(launch_broadcast_rows(P.f1.all(N), P.acat.view(N, 0, h16, 0, c8), s), "aspp broadcast")) return false;
+  if (!timed("aspp.broadcast_rows", N, h16, P.W / 16, s, [&] { return ck(launch_broadcast_rows(P.f1.all(N), P.acat.view(N, 0, h16, 0, c8), s), "aspp broadcast"); }))
+    return false;
   if (!run_conv(P.aspp2, P.e5.all(N), P.acat.view(N, 0, h16, c8, c8), s)) return false;
   for (int i = 0; i < 3; ++i)
     if (!run_conv(P.aspp_d[i], P.e5.all(N), P.acat.view(N, 0, h16, (2 + i) * c8, c8), s)) return false;
   if (!run_conv(P.bott, P.acat.all(N), P.ao.all(N), s)) return false;
   // decoders (lib/nets.py:35-37, lib/layers.py:51-64)
   launches += 2;
-  if (!ck(launch_upsample2x(P.ao.all(N), P.cat4.view(N, 0, H / 8, 0, 8 * n), s), "up4")) return false;
+  if (!timed("upsample2x", N, H / 8, P.W / 8, s, [&] { return ck(launch_upsample2x(P.ao.all(N), P.cat4.view(N, 0, H / 8, 0, 8 * n), s), "up4"); }))
+    return false;
   if (!run_conv(P.dec[0], P.cat4.all(N), P.d4.all(N), s)) return false;
-  if (!ck(launch_upsample2x(P.d4.all(N), P.cat3.view(N, 0, H / 4, 0, 6 * n), s), "up3")) return false;
+  if (!timed("upsample2x", N, H / 4, P.W / 4, s, [&] { return ck(launch_upsample2x(P.d4.all(N), P.cat3.view(N, 0, H / 4, 0, 6 * n), s), "up3"); }))
+    return false;
   if (!run_conv(P.dec[1], P.cat3.all(N), P.d3.all(N), s)) return false;
   if (!run_decoder(P.dec[2], P.d3.all(N), P.cat2, N, P.d2.view(N, 0, H / 2, 0, 2 * n), s)) return false;
   // LSTM branch -> channel 2n of d2 (lib/nets.py:38, lib/layers.py:124-133).  Its 128-step recurrence keeps only
@@ -548,13 +559,13 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
       return false;
   }
   launches += 5;
-  if (!ck(launch_lstm_inconv(P.d2.view(N, 0, H / 2, 0, 2 * n), Q.conv_w, Q.conv_bias, Q.l0, sl), "lstm conv"))
+  if (!timed("lstm.inconv", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_inconv(P.d2.view(N, 0, H / 2, 0, 2 * n), Q.conv_w, Q.conv_bias, Q.l0, sl), "lstm conv"); }))
     return false;
-  if (!ck(launch_gemm_nt(Q.l0, Q.wih, Q.bih, Q.xp, N * Q.T, 8 * Q.hid, Q.bins, sl), "lstm input projection"))
+  if (!timed("lstm.input_projection", N, H / 2, P.W / 2, sl, [&] { return ck(launch_gemm_nt(Q.l0, Q.wih, Q.bih, Q.xp, N * Q.T, 8 * Q.hid, Q.bins, sl), "lstm input projection"); }))
     return false;
-  if (!ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, sl), "lstm recurrence")) return false;
-  if (!ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, P.d2.all(N), 2 * n, sl),
-          "lstm dense"))
+  if (!timed("lstm.recurrence", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, sl), "lstm recurrence"); }))
+    return false;
+  if (!timed("lstm.dense", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, P.d2.all(N), 2 * n, sl), "lstm dense"); }))
     return false;
   // dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
   const int upc = P.e1_off;   // channels of d2 that are upsampled: 2n conv channels + the LSTM channel group
@@ -634,7 +645,7 @@ bool Engine::predict_mask(const float* mag, int N, float* mask_out, int offset, 
     p.stride_n = (int64_t)2 * nb * r; p.stride_c = (int64_t)nb * r; p.stride_bin = r;
     p.offset = offset; p.t_base0 = 0; p.t_limit = r; p.roi_t = 0; p.accumulate = 0;
     ++launches;
-    if (!ck(launch_mask_out(p, s), "mask_out")) return false;
+    if (!timed("mask_out", nb_now, max_bin, W, s, [&] { return ck(launch_mask_out(p, s), "mask_out"); })) return false;
   }
   return true;
 }
@@ -651,9 +662,9 @@ bool Engine::separate_windows(const float2* spec, int64_t T, const float* norm, 
     const int n_now = count - i < cfg_.max_batch ? count - i : cfg_.max_batch;
     const int g0 = first + i;
     ++launches;
-    if (!ck(launch_pack_mag_from_spec(spec, nb, T, max_bin, W, r, pad_l, g0, norm,
-                                      in3_.view(n_now, 0, max_bin, pos_x_, 2), s),
-            "pack"))
+    if (!timed("pack_mag_from_spec", n_now, max_bin, W, s, [&] {
+          return ck(launch_pack_mag_from_spec(spec, nb, T, max_bin, W, r, pad_l, g0, norm, in3_.view(n_now, 0, max_bin, pos_x_, 2), s), "pack");
+        }))
       return false;
     if (!forward(n_now, s)) return false;
     MaskOutParams p;
@@ -665,7 +676,7 @@ bool Engine::separate_windows(const float2* spec, int64_t T, const float* norm, 
     p.t_base0 = (int64_t)g0 * r - frame_shift;
     p.t_limit = mask_T; p.roi_t = r; p.accumulate = accumulate;
     ++launches;
-    if (!ck(launch_mask_out(p, s), "mask_out")) return false;
+    if (!timed("mask_out", n_now, max_bin, W, s, [&] { return ck(launch_mask_out(p, s), "mask_out"); })) return false;
   }
   return true;
 }
@@ -674,8 +685,8 @@ bool Engine::normaliser(const float2* spec, int64_t T, int mode, float* out, cud
   cudaSetDevice(cfg_.device);
   ++launches;
   const int64_t n = (int64_t)2 * bins() * T;
-  if (mode == 0) return ck(launch_absmax(spec, n, out, s), "absmax");
-  return ck(launch_lexmax_abs(spec, n, ws_lex_, out, s), "lexmax");
+  if (mode == 0) return timed("normaliser.absmax", 1, bins(), (int)T, s, [&] { return ck(launch_absmax(spec, n, out, s), "absmax"); });
+  return timed("normaliser.lexmax", 1, bins(), (int)T, s, [&] { return ck(launch_lexmax_abs(spec, n, ws_lex_, out, s), "lexmax"); });
 }
 
 // mask [2][bins][T]; the full window range of one track on this device (inference.py:70-77 / 83-98)
@@ -720,7 +731,7 @@ bool Engine::stft_range(const float* wave, int64_t L, float2* spec, int64_t T, i
     return false;
   }
   ++launches;
-  return ck(launch_stft(wave, L, cfg_.n_fft, cfg_.hop, spec, T, t0, t1, twiddle_, window_, s), "stft");
+  return timed("stft", 1, bins(), (int)(t1 - t0), s, [&] { return ck(launch_stft(wave, L, cfg_.n_fft, cfg_.hop, spec, T, t0, t1, twiddle_, window_, s), "stft"); });
 }
 
 bool Engine::normaliser_range(const float2* spec, int64_t T, int64_t t0, int64_t t1, float* out, cudaStream_t s) {
@@ -789,10 +800,11 @@ bool Engine::istft_range(const float2* spec, const float* mask, int64_t T, int64
   float* fa = ws_frames_;
   float* fb = mask ? ws_frames_ + (int64_t)2 * nfr * NF : nullptr;
   launches += 2;
-  if (!ck(launch_istft_frames(spec, mask, NF, T, f0, nfr, fa, fb, twiddle_, window_, s), "istft frames")) return false;
-  return ck(launch_istft_ola(fa, fb, NF, hop, T, f0, nfr, (int64_t)hop * k0, (int64_t)hop * k1, wave_a,
-                             mask ? wave_b : nullptr, window_, s),
-            "istft ola");
+  if (!timed("istft.frames", 1, bins(), (int)nfr, s, [&] { return ck(launch_istft_frames(spec, mask, NF, T, f0, nfr, fa, fb, twiddle_, window_, s), "istft frames"); }))
+    return false;
+  return timed("istft.overlap_add", 1, bins(), (int)nfr, s, [&] {
+    return ck(launch_istft_ola(fa, fb, NF, hop, T, f0, nfr, (int64_t)hop * k0, (int64_t)hop * k1, wave_a, mask ? wave_b : nullptr, window_, s), "istft ola");
+  });
 }
 
 // wave (2, L) in HBM -> instruments / vocals waves (2, hop*(T-1)) in HBM: the whole inference.py:147-176 path.

@@ -138,9 +138,20 @@ class Engine {
   std::map<std::string, HostTensor> sd_;
   std::vector<void*> allocs_;
   int last_n_ = 0;
+  // tc: 1 = tensor-core convolution, 0 = CUDA-core convolution, 2 = any other kernel of the path
   struct ProfRec { cudaEvent_t a, b; double flops; int tc; std::string name; int N, H, W; };
   bool profiling_ = false;
   std::vector<ProfRec> prof_;
+  int prof_begin(const std::string& name, int kind, double flops, int N, int H, int W, cudaStream_t s);
+  void prof_end(int idx, cudaStream_t s);
+  // a non-convolution launch, bracketed by a CUDA-event pair while profiling is on
+  template <class F>
+  bool timed(const char* name, int N, int H, int W, cudaStream_t s, F&& launch) {
+    const int i = prof_begin(name, 2, 0.0, N, H, W, s);
+    const bool ok = launch();
+    prof_end(i, s);
+    return ok;
+  }
 
   // whole-track workspace (grow-only)
   float2* ws_spec_ = nullptr; int64_t ws_spec_cap_ = 0;

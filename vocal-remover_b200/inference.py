@@ -170,10 +170,16 @@ def main():
     p.add_argument('--output_dir', '-o', type=str, default="")
     args = p.parse_args()
 
-    print('loading model...', end=' ')
+    # unsupported surfaces fail before any heavy work (model load, audio decode, output directory)
+    if args.output_image:
+        raise NotImplementedError('--output_image (debug JPGs, lib/utils.py) is outside the B200 hot path')
     if not torch.cuda.is_available():
         raise RuntimeError('no CUDA device: the B200 build of vocal-remover has no CPU path')
-    # the reference's default (--gpu -1) means CPU; here it means "the first GPU"
+    if args.gpu < 0:
+        # the reference's default (--gpu -1) means CPU; this build has no CPU path
+        print('note: --gpu {} selects the CPU in the reference; this build has no CPU path and uses cuda:0'.format(args.gpu))
+
+    print('loading model...', end=' ')
     device = torch.device('cuda:{}'.format(max(args.gpu, 0)))
     model = nets.CascadedNet(args.n_fft, args.hop_length, 32, 128)
     model.load_state_dict(torch.load(args.pretrained_model, map_location='cpu'))
@@ -204,9 +210,6 @@ def main():
         output_dir = output_dir.rstrip('/') + '/'
         os.makedirs(output_dir, exist_ok=True)
     print('done')
-
-    if args.output_image:
-        raise NotImplementedError('--output_image (debug JPGs, lib/utils.py) is outside the B200 hot path')
 
     print('stft of wave source, separation, inverse stft of instruments and vocals...', end=' ')
     wave_inst, wave_voc = sp.separate_wave(X, tta=args.tta)

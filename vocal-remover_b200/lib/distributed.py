@@ -63,7 +63,22 @@ def gather_blocks(block, world, rank, group=None):
     return gathered
 
 
-_shared = {}   # (ctx id, tag, bytes) -> (device pointer, owner flag)
+# Per-context caches, grow-only (a new track length re-uses the buffers when it fits, otherwise replaces them):
+#   ('ipc', ctx, tag) -> (device pointer, owner flag, capacity in bytes)   buffers in rank 0's HBM mapped on every rank
+#   ('ws', ctx) / ('hostws', ctx) -> (capacity, tensors...)                per-rank workspaces
+# Keys hold the context object itself (not id(ctx), which can be recycled after a context is closed); release(ctx)
+# drops everything a context owns (IPC mappings are closed with vr_shared_close).
+_shared = {}
+_calls = {}    # ctx -> number of sharded device-resident calls (selects one of two stem buffer sets, see below)
+
+
+def release(ctx):
+    """Free the cached workspaces and close the IPC mappings of ``ctx`` (call before closing the context)."""
+    for key in [k for k in _shared if k[1] is ctx]:
+        val = _shared.pop(key)
+        if key[0] == 'ipc':
+            ctx.lib.vr_shared_close(ctx.handle, val[0], 1 if val[1] else 0)
+    _calls.pop(ctx, None)
 
 
 class _RawCudaArray(object):
@@ -77,9 +92,12 @@ class _RawCudaArray(object):
 def _shared_buffer(ctx, tag, nbytes, world, rank, dev, group):
     """A buffer in rank 0's HBM, mapped on every rank (cached per context, tag and size)."""
     import torch.distributed as dist
-    key = (id(ctx), tag, int(nbytes))
+    key = ('ipc', ctx, tag)
     if key in _shared:
-        return _shared[key][0]
+        if _shared[key][2] >= int(nbytes):
+            return _shared[key][0]
+        old = _shared.pop(key)   # same decision on every rank: sizes derive from the track length only
+        ctx.check(ctx.lib.vr_shared_close(ctx.handle, old[0], 1 if old[1] else 0), 'vr_shared_close')
     handle = ctypes.create_string_buffer(64)
     ptr = _native.c_vp()
     if rank == 0:
@@ -89,7 +107,7 @@ def _shared_buffer(ctx, tag, nbytes, world, rank, dev, group):
     if rank != 0:
         raw = bytes(t.cpu().tolist())
         ctx.check(ctx.lib.vr_shared_open(ctx.handle, raw, ctypes.byref(ptr)), 'vr_shared_open')
-    _shared[key] = (ptr, rank == 0)
+    _shared[key] = (ptr, rank == 0, int(nbytes))
     return ptr
 
 
@@ -149,13 +167,15 @@ def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=N
     T = 1 + L // hop
     Lo = hop * (T - 1)
     first, count, roi, f0, f1, a, b, k0, k1 = shard_plan(T, sp.cropsize, sp.offset, world, rank)
-    st = _native.stream_ptr()
     with torch.cuda.device(dev):
-        key = ('ws', id(ctx), T)
-        if key not in _shared:
-            _shared[key] = (torch.empty((2, bins, T), dtype=torch.complex64, device=dev),
-                            torch.empty((2, bins, T), dtype=torch.float32, device=dev))
-        spec, mask = _shared[key]
+        st = _native.stream_ptr()
+        key = ('ws', ctx)
+        if key not in _shared or _shared[key][0] < T:
+            _shared.pop(key, None)
+            _shared[key] = (T, torch.empty((2 * bins * T,), dtype=torch.complex64, device=dev),
+                            torch.empty((2 * bins * T,), dtype=torch.float32, device=dev))
+        spec = _shared[key][1][:2 * bins * T].view(2, bins, T)
+        mask = _shared[key][2][:2 * bins * T].view(2, bins, T)
         norm = torch.zeros(1, dtype=torch.float32, device=dev)
         if tta:
             # inference.py:87,94: the normaliser is |lexicographic complex max| of the whole (padded) track
@@ -199,8 +219,13 @@ def _separate_wave_sharded(sp, d_wave, world, rank, group, to_rank0, local_out=N
         if recv_col is not None:
             mask[:, :, f1].copy_(recv_col)
         if to_rank0:
-            inst_ptr = _shared_buffer(ctx, 'inst', 2 * Lo * 4, world, rank, dev, group)
-            voc_ptr = _shared_buffer(ctx, 'voc', 2 * Lo * 4, world, rank, dev, group)
+            # Two stem buffer sets, used alternately: the stems a call returns on rank 0 stay valid until the call after
+            # next, whose remote stores are ordered (by the completion all-reduce of the call in between, which rank 0
+            # enqueues after whatever it launched on the returned tensors) behind rank 0's reads - no entry barrier.
+            which = _calls.get(ctx, 0) & 1
+            _calls[ctx] = _calls.get(ctx, 0) + 1
+            inst_ptr = _shared_buffer(ctx, 'inst%d' % which, 2 * Lo * 4, world, rank, dev, group)
+            voc_ptr = _shared_buffer(ctx, 'voc%d' % which, 2 * Lo * 4, world, rank, dev, group)
         else:
             inst_ptr, voc_ptr = _native.ptr(local_out[0]), _native.ptr(local_out[1])
         if k1 > k0:
@@ -315,13 +340,16 @@ def separate_wave_host(sp, h_wave, h_inst, h_voc, tta=False, world=1, rank=0, gr
         return (0, h_inst.shape[1]) if rank == 0 else (0, 0)
     _, _, _, _, _, a, b, _, _ = shard_plan(T, sp.cropsize, sp.offset, world, rank)
     with torch.cuda.device(dev):
-        key = ('hostws', id(sp._ctx()), L)
-        if key not in _shared:
-            Lo = hop * (T - 1)
-            _shared[key] = (torch.empty((2, L), dtype=torch.float32, device=dev),
-                            torch.empty((2, Lo), dtype=torch.float32, device=dev),
-                            torch.empty((2, Lo), dtype=torch.float32, device=dev))
-        d_wave, d_inst, d_voc = _shared[key]
+        key = ('hostws', sp._ctx())
+        Lo = hop * (T - 1)
+        if key not in _shared or _shared[key][0] < L:
+            _shared.pop(key, None)
+            _shared[key] = (L, torch.empty((2 * L,), dtype=torch.float32, device=dev),
+                            torch.empty((2 * L,), dtype=torch.float32, device=dev),
+                            torch.empty((2 * L,), dtype=torch.float32, device=dev))
+        d_wave = _shared[key][1][:2 * L].view(2, L)
+        d_inst = _shared[key][2][:2 * Lo].view(2, Lo)
+        d_voc = _shared[key][3][:2 * Lo].view(2, Lo)
         if b > a:   # samples read by frames [a, b)
             w0 = max(0, a * hop - n_fft // 2)
             w1 = min(L, (b - 1) * hop + n_fft // 2)
