@@ -91,3 +91,25 @@ def test_decoder_fused_upsample_vs_staged_and_torch(case):
     assert (outs[1] - ref.float()).abs().max().item() < tol
     # same interpolation arithmetic, same products: the two paths agree to accumulation-order noise
     assert (outs[0] - outs[1]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_row_kernel_64_wide_tile_on_plain_convolution():
+    """The 64-output-channel tile of the row kernel (single accumulator set, N = 192 MMAs) is used by the net only for
+    the fused decoder layers; vr_debug_set(2, 1) selects it for a plain TMA-fed convolution as well."""
+    from lib import _native
+    case = (2, 64, 16, 128, 64, 3, 1, (1, 1), 2)
+    N, Cin, H, W, Cout, k, stride, dil, act = case
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ctx = _native.Context(0, 2048, 1024, 32, 128, 256, 1, 0)
+    ref = _ref_conv(x, w, b, k, stride, dil, act)
+    ctx.lib.vr_debug_set(2, 1)
+    try:
+        y = _run_debug_conv(ctx, x, w, b, k, stride, dil, act, 1)
+    finally:
+        ctx.lib.vr_debug_set(2, 0)
+    err = (y - ref).abs().max().item()
+    record_parity('conv_tcgen05_rows64_%s' % '_'.join(str(v) for v in case).replace(' ', ''), err / max(1.0, ref.abs().max().item()), 2e-4)
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), err

@@ -403,10 +403,10 @@ bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs) {
 }
 
 cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err,
-                      const ActView* up_src) {
+                      const ActView* up_src, const ActView* extra) {
   TcConv& tc = *L.tc;
-  if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err, up_src);
-  if (up_src) {
+  if (tc_rows_supported(L, tc, in, out)) return tc_rows_launch(L, tc, in, out, s, err, up_src, extra);
+  if (up_src || extra) {
     err = "tc_launch: fused upsample is only implemented in the row-streaming kernel";
     return cudaErrorInvalidValue;
   }

@@ -197,19 +197,19 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     err = "unsupported geometry: band height and cropsize must be multiples of 16 and nout a multiple of 16";
     return false;
   }
-  // lstm channel + 15 zero channels keep every slice 32-byte aligned (full-sector 256-bit epilogue stores); with the
-  // fused decoder upsample the group is a whole 32-channel chunk so that chunks are either upsampled or skip data
-  // When dec1's upsample is certain to be fused (tensor-core mode, row kernel with 32-channel chunks), the up(h, lstm)
-  // slice is never materialised: cat1 then holds ONLY the skip tensor e1, dense, so that the row kernel's TMA reads of
-  // it are contiguous (inside the wide concat buffer e1 was a 32..64-byte island per 160..256-byte pixel and the
-  // 256-byte L2 promotion over-fetched: 292 MB of DRAM reads for 134 MB of operands on stg1_low.dec1).
+  // Layouts of the dec1 input (see BaseNetPlan::skip_only in engine.h).  The fused layout needs the row kernel with
+  // dec1's up-sampled half (h, 2n channels) in whole 32-channel chunks.
   P.skip_only = cfg_.conv_mode == 0 && g_tc_debug[5] == 1 && g_tc_debug[1] == 0 &&
                 (2 * n) % 32 == 0 && W % 128 == 0 && H % 8 == 0;
-  const int lg = P.skip_only ? 32 : 16;
-  const int c1 = round_up(3 * n + lg, 16);
-  P.e1_off = 2 * n + lg;                       // position of e1 in dec1's reduction (weight) order
-  P.e1_coff = P.skip_only ? 0 : P.e1_off;      // position of e1 in the cat1 buffer
-  P.cat1 = make_buffer(Nb, H, W, P.skip_only ? round_up(n, 16) : c1);
+  const int lg = 16;   // the lstm channel + 15 zeros keep every slice 32-byte aligned (full-sector 256-bit stores)
+  P.lstm_own = P.skip_only && n % 32 == 0;
+  const int c1 = P.skip_only ? 2 * n + round_up(n, 32) + (P.lstm_own ? lg : 0) : round_up(3 * n + lg, 16);
+  P.e1_off = P.skip_only ? 2 * n : 2 * n + lg;      // position of e1 in dec1's reduction (weight) order
+  P.e1_coff = P.skip_only ? 0 : P.e1_off;           // position of e1 in the cat1 buffer
+  P.lstm_coff = !P.skip_only ? 2 * n : P.lstm_own ? 0 : n;
+  P.cat1 = make_buffer(Nb, H, W, !P.skip_only ? c1 : P.lstm_own ? n : round_up(n + lg, 32));
+  if (P.skip_only) P.lstm_lo = make_buffer(Nb, H / 2, W / 2, lg);
+  if (P.lstm_own) P.lstm_up = make_buffer(Nb, H, W, lg);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
   P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
@@ -224,7 +224,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.ao = make_buffer(Nb, H / 16, W / 16, 8 * n);
   P.d4 = make_buffer(Nb, H / 8, W / 8, 6 * n);
   P.d3 = make_buffer(Nb, H / 4, W / 4, 4 * n);
-  P.d2 = make_buffer(Nb, H / 2, W / 2, 2 * n + lg);
+  P.d2 = make_buffer(Nb, H / 2, W / 2, P.skip_only ? 2 * n : 2 * n + lg);
   if (!P.d2.hi || !P.cat1.hi) return false;
 
   if (!make_conv(P.enc1, prefix + ".enc1", in_perm, cin_pad, 3, 1, 1, 1, ACT_RELU)) return false;
@@ -251,13 +251,15 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     return false;
   if (!make_conv(P.dec[1], prefix + ".dec3.conv1", identity_perm(10 * n, 10 * n), 10 * n, 3, 1, 1, 1, ACT_RELU))
     return false;
+  P.dec[2].rows_wide = true;   // dec2's upsample is fused into the row kernel whenever 4n is a multiple of 32
   if (!make_conv(P.dec[2], prefix + ".dec2.conv1", identity_perm(6 * n, 6 * n), 6 * n, 3, 1, 1, 1, ACT_RELU))
     return false;
   {
     // dec1 input in the reference: cat[ up(cat[h (2n), lstm (1)]) , e1 (n) ]  (lib/nets.py:38-39, layers.py:52-56)
-    // packed as [ up(h) 2n | up(lstm) 1 | 15 or 31 zeros | e1 n | zeros ]
+    // packed as [ up(h) 2n | up(lstm) 1 | 15 zeros | e1 n | zeros ], or (skip_only) [ up(h) 2n | e1 n | up(lstm) 1 | zeros ]
     std::vector<int> perm((size_t)c1, -1);
-    for (int i = 0; i < 2 * n + 1; ++i) perm[(size_t)i] = i;
+    for (int i = 0; i < 2 * n; ++i) perm[(size_t)i] = i;
+    perm[(size_t)(!P.skip_only ? 2 * n : P.lstm_own ? 2 * n + round_up(n, 32) : 2 * n + n)] = 2 * n;
     for (int i = 0; i < n; ++i) perm[(size_t)(P.e1_off + i)] = 2 * n + 1 + i;
     if (!make_conv(P.dec[3], prefix + ".dec1.conv1", perm, c1, 3, 1, 1, 1, ACT_RELU)) return false;
   }
@@ -469,21 +471,22 @@ bool Engine::profile_dump(std::string& text) {
   return true;
 }
 
-bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src) {
+bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src,
+                      const ActView* extra) {
   ++launches;
   const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
   // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
   const int pi = prof_begin(up_src ? L.name + "+up" : L.name, use_tc ? 1 : 0,
                             2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k, out.N, out.H, out.W, s);
-  bool ok = run_conv_inner(L, in, out, use_tc, s, up_src);
+  bool ok = run_conv_inner(L, in, out, use_tc, s, up_src, extra);
   prof_end(pi, s);
   return ok;
 }
 
 bool Engine::run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s,
-                            const ActView* up_src) {
-  if (use_tc) return ck(tc_launch(L, in, out, s, err, up_src), L.name.c_str());
-  if (up_src) {
+                            const ActView* up_src, const ActView* extra) {
+  if (use_tc) return ck(tc_launch(L, in, out, s, err, up_src, extra), L.name.c_str());
+  if (up_src || extra) {
     err = "internal: fused upsample requested for a CUDA-core convolution";
     return false;
   }
@@ -565,9 +568,30 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
     return false;
   if (!timed("lstm.recurrence", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, sl), "lstm recurrence"); }))
     return false;
-  if (!timed("lstm.dense", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, P.d2.all(N), 2 * n, sl), "lstm dense"); }))
+  // the LSTM channel at half resolution: channel 2n of d2 (staged layout) or channel 0 of lstm_lo (fused layout)
+  const ActView lstm_dst = P.skip_only ? P.lstm_lo.all(N) : P.d2.all(N);
+  const int lstm_ch = P.skip_only ? 0 : 2 * n;
+  if (!timed("lstm.dense", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, lstm_dst, lstm_ch, sl), "lstm dense"); }))
     return false;
-  // dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
+  if (P.skip_only) {
+    // fused layout: up(lstm) -> its 8-channel group of cat1 (small kernel on the LSTM's stream), then the row kernel
+    // reads cat1 = [e1 | up(lstm)] by TMA and produces up(h) itself from d2
+    ++launches;
+    const ActView lstm_full = P.lstm_own ? P.lstm_up.all(N) : P.cat1.view(N, 0, H, P.lstm_coff, 16);
+    if (!timed("lstm.upsample2x", N, H, P.W, sl, [&] { return ck(launch_upsample2x(P.lstm_lo.all(N), lstm_full, sl), "lstm upsample"); }))
+      return false;
+    if (overlap) {
+      if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join") || !ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join"))
+        return false;
+    }
+    const ActView h = P.d2.all(N);
+    if (!tc_can_fuse_upsample(P.dec[3], P.cat1.all(N), out, h)) {
+      err = "internal: " + P.prefix + ".dec1 was laid out for the fused upsample but the fused kernel is not available";
+      return false;
+    }
+    return run_conv(P.dec[3], P.cat1.all(N), out, s, &h, P.lstm_own ? &lstm_full : nullptr);
+  }
+  // staged layout: dec1 on cat[up(h, lstm), e1] (lib/nets.py:39)
   const int upc = P.e1_off;   // channels of d2 that are upsampled: 2n conv channels + the LSTM channel group
   if (overlap) {
     if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join")) return false;
@@ -575,10 +599,6 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
       // fused: the convolution reads d2 (incl. the LSTM channel) itself, so it simply waits for the side stream
       if (!ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join")) return false;
       return run_decoder(P.dec[3], P.d2.all(N), P.cat1, N, out, s);
-    }
-    if (P.skip_only) {
-      err = "internal: " + P.prefix + ".dec1 was laid out for the fused upsample but the fused kernel is not available";
-      return false;
     }
     ++launches;
     if (!ck(launch_upsample2x(P.d2.view(N, 0, H / 2, 0, 2 * n), P.cat1.view(N, 0, H, 0, 2 * n), s), "up1")) return false;
@@ -851,6 +871,7 @@ bool Engine::debug_conv(const float* x_nchw, int N, int Cin, int H, int W, const
   Buffer bout = make_buffer(N, Ho, Wo, round_up(Cout, 8));
   ConvLayer L;
   L.name = "debug_conv";
+  L.rows_wide = g_tc_debug[2] == 1;   // vr_debug_set(2, 1): exercise the 64-wide row tile on a plain convolution
   L.Cin = Cin; L.CinPad = cin_pad; L.Cout = Cout; L.CoutPad = round_up(Cout, 8);
   L.k = k; L.stride = stride; L.dil_h = dil_h; L.dil_w = dil_w; L.act = act;
   const int taps = k * k;
@@ -911,6 +932,7 @@ bool Engine::debug_decoder(const float* low_nchw, int N, int Cl, int h, int w, c
   Buffer bout = make_buffer(N, H, W, round_up(Cout, 16));
   ConvLayer L;
   L.name = "debug_decoder";
+  L.rows_wide = true;
   L.Cin = Cin; L.CinPad = cin_pad; L.Cout = Cout; L.CoutPad = round_up(Cout, 8);
   L.k = 3; L.stride = 1; L.dil_h = 1; L.dil_w = 1; L.act = act;
   std::vector<float> hw((size_t)Cout * Cin * 9), hb((size_t)Cout);

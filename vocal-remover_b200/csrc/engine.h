@@ -48,6 +48,7 @@ struct ConvLayer {
   float* bias = nullptr;   // device fp32 [CoutPad]
   std::vector<float> w_host;     // packed copy kept for the tensor-core packer
   std::vector<float> bias_host;
+  bool rows_wide = false;        // row kernel: 64 output channels per tile (decoder layers whose upsample is fused)
   std::shared_ptr<TcConv> tc;    // null -> CUDA-core kernel
 };
 
@@ -71,10 +72,18 @@ struct BaseNetPlan {
   int n = 0, H = 0, W = 0;
   ConvLayer enc1, enc_a[4], enc_b[4], aspp1, aspp2, aspp_d[3], bott, dec[4];   // dec[0]=dec4 .. dec[3]=dec1
   LstmPlan lstm;
-  bool skip_only = false;   // cat1 holds only e1 (dec1's upsample is fused into the row kernel)
+  // skip_only: dec1's upsample of h is fused into the row kernel and d2 = [h 2n] only; the single LSTM channel is
+  // up-sampled by a small kernel from lstm_lo (half resolution, 16-channel group) into a 16-channel group at full
+  // resolution: channels [n, n+16) of cat1 = [e1 n | up(lstm) 1 + 15 zeros] when e1 leaves room in its chunk (n = 16),
+  // else the buffer lstm_up of its own (n = 32: cat1 = [e1 n] stays dense for enc2.conv1, and the row kernel reads the
+  // group as its last chunk through a second tensor map).  Otherwise (CUDA-core validation mode, nets whose
+  // 2n is not a multiple of 32): cat1 = [up(h) 2n | up(lstm) 1 + 15 zeros | e1 n | pad], d2 = [h 2n | lstm 1 | zeros].
+  bool skip_only = false;
   int e1_coff = 0;          // channel offset of e1 inside cat1
-  Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2;
-  int e1_off = 0;   // channel offset of e1 inside cat1
+  int lstm_coff = 0;        // skip_only: channel offset of the up-sampled LSTM channel inside cat1 (or 0 in lstm_up)
+  bool lstm_own = false;    // skip_only: the up-sampled LSTM group lives in lstm_up, not in cat1
+  Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2, lstm_lo, lstm_up;
+  int e1_off = 0;   // position of e1 in dec1's reduction (weight) order
 };
 
 struct Config {
@@ -184,9 +193,10 @@ class Engine {
                  int dh, int dw, int act);
   bool build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, const std::vector<int>& in_perm, int cin_pad,
                      int n, int H, int W, int nin_lstm, int nout_lstm);
-  bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src = nullptr);
+  bool run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, const ActView* up_src = nullptr,
+                const ActView* extra = nullptr);
   bool run_conv_inner(ConvLayer& L, const ActView& in, const ActView& out, bool use_tc, cudaStream_t s,
-                      const ActView* up_src);
+                      const ActView* up_src, const ActView* extra);
   // Decoder (lib/layers.py:51-64): upsample `low` into channels [0, low.C) of `cat`, then conv(cat) -> out; the
   // upsample is fused into the convolution's operand producer when the row kernel can do it
   bool run_decoder(ConvLayer& L, const ActView& low, const Buffer& cat, int N, const ActView& out, cudaStream_t s);
@@ -201,7 +211,7 @@ class Engine {
 bool tc_supported(const ConvLayer& L, const ActView& in, const ActView& out);
 bool tc_prepare(ConvLayer& L, std::string& err, std::vector<void*>& allocs);
 cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaStream_t s, std::string& err,
-                      const ActView* up_src = nullptr);
+                      const ActView* up_src = nullptr, const ActView* extra = nullptr);
 bool tc_can_fuse_upsample(const ConvLayer& L, const ActView& in, const ActView& out, const ActView& up_src);
 
 }  // namespace vr

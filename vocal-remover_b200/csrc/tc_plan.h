@@ -19,6 +19,7 @@ struct TcRowsPlan {   // row-streaming variant: 3x3, stride 1, dilation 1, W % 1
   float* bias = nullptr;      // [n_tiles*BN]
   CUtensorMap map_b;
   std::map<ViewKey, CUtensorMap> map_a;
+  std::map<ViewKey, CUtensorMap> map_l;   // second activation map (the chunk read from its own buffer)
 };
 
 struct TcConv {
@@ -41,8 +42,9 @@ float tc_bf2f(uint16_t h);
 bool tc_rows_prepare(ConvLayer& L, TcConv& tc, std::string& err, std::vector<void*>& allocs);
 bool tc_rows_supported(const ConvLayer& L, const TcConv& tc, const ActView& in, const ActView& out);
 cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const ActView& out, cudaStream_t s,
-                           std::string& err, const ActView* up_src = nullptr);
+                           std::string& err, const ActView* up_src = nullptr, const ActView* extra = nullptr);
 void tc_rows_set_attributes(int max_smem);
+int tc_rows_read_trace(unsigned long long* out, long long capacity);
 
 // Properties of the CURRENT device, cached per device ordinal.  The first use on a device also opts the tensor-core
 // kernels in to their dynamic shared memory there (cudaFuncSetAttribute is per device, so a process that drives
@@ -53,7 +55,7 @@ struct TcDevice {
 };
 const TcDevice& tc_device();
 
-// validation knobs (vr_debug_set): [1] = 1 disables the row kernel, [4] = k: k of the row slots feed the interpolation
+// validation knobs (vr_debug_set): [0] = 1: CTA 0 of the row kernel records a timeline (vr_debug_trace), [2] = 1: vr_debug_conv uses the 64-wide row tile, [1] = 1 disables the row kernel, [4] = k: k of the row slots feed the interpolation
 // warps (default half), [5] = 1 (default): decoder upsample fused into the row kernel, [6] = 1 (default): the row
 // kernel skips channel groups whose weights are all zero; the other entries are unused
 extern int g_tc_debug[8];
