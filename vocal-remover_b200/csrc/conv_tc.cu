@@ -47,8 +47,18 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------
+// KB: channels per operand sub-tile (64 / 32 / 16 = SWIZZLE_128B / 64B / 32B); a pipeline stage holds 64 / KB sub-tiles.
+// The producer and the MMA issuer are single elected lanes running their whole loop nests with compile-time operand
+// strides (see conv_tc_rows.cu: the tensor pipe queues only a few MMAs, so scalar work between the last MMA of a stage
+// and the first of the next one is a bubble; ~500 cycles per stage were measured with the per-stage election and
+// run-time strides of the first version).
+template <int KB>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  constexpr int SUBS = 64 / KB;
+  constexpr int kSteps = KB / 16;
+  constexpr uint32_t kAPlane = 128 * KB * 2;     // one plane of an A sub-tile (128 pixels x KB channels)
+  constexpr uint32_t kASub = 2 * kAPlane;        // hi + lo
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages];
   __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
@@ -60,10 +70,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = p.SUBS * (p.a_sub_bytes + p.b_sub_bytes);
-  const int b_region = p.SUBS * p.a_sub_bytes;   // B sub-tiles follow the A sub-tiles inside a stage
+  const uint32_t b_sub_bytes = (uint32_t)p.b_sub_bytes;
+  const uint32_t stage_bytes = (uint32_t)SUBS * (kASub + b_sub_bytes);
+  constexpr uint32_t b_region = (uint32_t)SUBS * kASub;   // B sub-tiles follow the A sub-tiles inside a stage
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int num_iters = (p.total_sub + p.SUBS - 1) / p.SUBS;
+  const int num_iters = (p.total_sub + SUBS - 1) / SUBS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -91,38 +102,42 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
-    {
+    // ===================== TMA producer (one elected lane runs the whole loop nest) =====================
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const int mt = tile / p.n_tiles;
         const int w0 = (mt % p.tiles_w) * p.Wt;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.Ht;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.Nt;
+        const int wbase = w0 * p.stride - p.pad_w, hbase = h0 * p.stride - p.pad_h;
+        const int nrow = nt * p.BN;
+        int cc = 0, kw = 0, kh = 0, sub = 0;   // (tap, channel chunk) of the next sub-tile, advanced without divisions
         for (int it = 0; it < num_iters; ++it) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          const int sub0 = it * p.SUBS;
-          const int nsub = min(p.SUBS, p.total_sub - sub0);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          const uint32_t sbase = smem_base + (uint32_t)(stage * stage_bytes);
-          if (elect_one_sync()) mbar_expect_tx(full, (uint32_t)(nsub * (p.a_sub_bytes + p.b_sub_bytes)));
-          __syncwarp();
-          for (int j = 0; j < nsub; ++j) {
-            const int sub = sub0 + j;
-            const int tap = sub / p.cchunks;
-            const int cc = sub - tap * p.cchunks;
-            const int kh = tap / p.KW;
-            const int kw = tap - kh * p.KW;
-            if (elect_one_sync()) {
-              tma_load_5d(sbase + (uint32_t)(j * p.a_sub_bytes), &tmA, cc * p.KB,
-                          w0 * p.stride - p.pad_w + kw * p.dil_w, h0 * p.stride - p.pad_h + kh * p.dil_h, n0, 0, full);
-              tma_load_3d(sbase + (uint32_t)(b_region + j * p.b_sub_bytes), &tmB, tap * p.CinPadTC + cc * p.KB,
-                          nt * p.BN, 0, full);
+          mbar_wait(empty0 + (uint32_t)stage * 8u, phase ^ 1u);
+          const int nsub = min(SUBS, p.total_sub - sub);
+          const uint32_t full = full0 + (uint32_t)stage * 8u;
+          const uint32_t sbase = smem_base + (uint32_t)stage * stage_bytes;
+          mbar_expect_tx(full, (uint32_t)nsub * (kASub + b_sub_bytes));
+#pragma unroll
+          for (int j = 0; j < SUBS; ++j) {
+            if (j < nsub) {
+              tma_load_5d(sbase + (uint32_t)j * kASub, &tmA, cc * KB, wbase + kw * p.dil_w, hbase + kh * p.dil_h, n0, 0, full);
+              tma_load_3d(sbase + b_region + (uint32_t)j * b_sub_bytes, &tmB, (kh * p.KW + kw) * p.CinPadTC + cc * KB, nrow, 0,
+                          full);
+              ++sub;
+              if (++cc == p.cchunks) {
+                cc = 0;
+                if (++kw == p.KW) {
+                  kw = 0;
+                  ++kh;
+                }
+              }
             }
           }
-          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -130,61 +145,62 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
-    {
+    // ===================== MMA issuer (one elected lane runs the whole loop nest) =====================
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const int ksteps = p.KB / 16;
       const uint32_t dhi = desc_hi(p.sbo_bytes, p.layout_type);
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      const uint32_t b_sub16 = b_sub_bytes >> 4;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&bar_tempty[acc]), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * p.BN);   // [D1 | D2], see the issue loop
-        uint32_t accumulate = 0;
+        mbar_wait(full0 + (uint32_t)stage * 8u, phase);
+        int sub = 0;
         for (int it = 0; it < num_iters; ++it) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tc_fence_after();
-          const int nsub = min(p.SUBS, p.total_sub - it * p.SUBS);
-          const uint32_t sbase = smem_base + (uint32_t)(stage * stage_bytes);
-          // one elected lane issues the whole stage (ptxas keeps the region branch-free after elect.sync)
-          if (elect_one_sync()) {
-            for (int j = 0; j < nsub; ++j) {
-              // descriptor low words (start address >> 4); a k-step of 16 bf16 = 32 B = +2
-              const uint32_t a_hi = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes));
-              const uint32_t a_lo = desc_lo(sbase + (uint32_t)(j * p.a_sub_bytes + p.a_plane_bytes));
-              const uint32_t b_hi = desc_lo(sbase + (uint32_t)(b_region + j * p.b_sub_bytes));
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k >= ksteps) break;
-                const uint32_t ko = (uint32_t)(2 * k);
-                // The hi and lo weight planes are adjacent in the stage ([BN rows hi][BN rows lo], same pitch), so
-                // A_hi meets both in ONE N = 2*BN instruction: D1 += A_hi*B_hi, D2 += A_hi*B_lo.  A second
-                // N = BN instruction adds A_lo*B_hi to D1.  Two instructions and one shared-memory pass over A_hi
-                // per k-step instead of three; the epilogue adds D1 + D2.
-                umma_bf16_w(d_tmem, a_hi + ko, b_hi + ko, dhi, p.idesc2, accumulate);
-                umma_bf16_w(d_tmem, a_lo + ko, b_hi + ko, dhi, p.idesc, 1u);
-                accumulate = 1u;
-              }
-            }
-            umma_commit(smem_u32(&bar_empty[stage]));   // frees the slot once the MMAs have read it
-          }
-          accumulate = 1u;
-          __syncwarp();
+          const int nsub = min(SUBS, p.total_sub - sub);
+          sub += nsub;
+          const uint32_t sdesc = desc_lo(smem_base + (uint32_t)stage * stage_bytes);
+          const uint32_t empty = empty0 + (uint32_t)stage * 8u;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
+          // The hi and lo weight planes are adjacent in the stage ([BN rows hi][BN rows lo], same pitch), so A_hi meets
+          // both in ONE N = 2*BN instruction: D1 += A_hi*B_hi, D2 += A_hi*B_lo.  A second N = BN instruction adds
+          // A_lo*B_hi to D1.  Two instructions and one shared-memory pass over A_hi per k-step instead of three; the
+          // epilogue adds D1 + D2.  The wait for the NEXT stage is issued before the last pair of this one, so that it
+          // overlaps the products still queued in the tensor pipe.
+#pragma unroll
+          for (int j = 0; j < SUBS; ++j) {
+            if (j < nsub) {
+              const uint32_t a_hi = sdesc + (uint32_t)((j * kASub) >> 4);
+              const uint32_t a_lo = a_hi + (kAPlane >> 4);
+              const uint32_t b_hi = sdesc + (b_region >> 4) + (uint32_t)j * b_sub16;
+#pragma unroll
+              for (int k = 0; k < kSteps; ++k) {
+                if (j == nsub - 1 && k == kSteps - 1 && it + 1 < num_iters) mbar_wait(full0 + (uint32_t)stage * 8u, phase);
+                const uint32_t acc_flag = (it | j | k) ? 1u : 0u;
+                umma_bf16_w(d_tmem, a_hi + 2u * k, b_hi + 2u * k, dhi, p.idesc2, acc_flag);
+                umma_bf16_w(d_tmem, a_lo + 2u * k, b_hi + 2u * k, dhi, p.idesc, 1u);
+              }
+            }
+          }
+          umma_commit(empty);   // frees the slot once the MMAs have read it
         }
-        if (elect_one_sync()) umma_commit(smem_u32(&bar_tfull[acc]));       // accumulator complete -> epilogue
+        umma_commit(smem_u32(&bar_tfull[acc]));       // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1) =====================
     const int q = warp & 3;
@@ -263,7 +279,9 @@ const TcDevice& tc_device() {
     if (cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return none;
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - 2048);
+    cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - 2048);
+    cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - 2048);
+    cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem - 2048);
     tc_rows_set_attributes(d.max_smem);
     d.ok = true;
   }
@@ -476,7 +494,12 @@ cudaError_t tc_launch(ConvLayer& L, const ActView& in, const ActView& out, cudaS
   p.tmem_cols = cols;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < dv.num_sms ? total_tiles : dv.num_sms;
-  conv_tc_kernel<<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
+  if (tc.KB == 64)
+    conv_tc_kernel<64><<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
+  else if (tc.KB == 32)
+    conv_tc_kernel<32><<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
+  else
+    conv_tc_kernel<16><<<grid, kThreads, dyn, s>>>(it->second, tc.map_b, p);
   return cudaGetLastError();
 }
 

@@ -150,6 +150,46 @@ cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// Single-channel variant for the LSTM branch (lib/nets.py:38, layers.py:52): channel 0 of `in` is up-sampled with the same
+// arithmetic as upsample2x_kernel and written as channel 0 of a 16-channel group whose other channels are zeros (one full
+// 32-byte sector per plane and pixel).  The generic kernel spent its time blending the 15 zero channels.
+__global__ void __launch_bounds__(256) upsample2x_c1_kernel(ActView in, ActView out, float sh, float sw) {
+  const int wo = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wo >= out.W) return;
+  const int n = blockIdx.y / out.H;
+  const int ho = blockIdx.y - n * out.H;
+  const float fy = sh * ho, fx = sw * wo;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const int64_t base = (int64_t)n * in.sn;
+  const int64_t r0 = base + (int64_t)y0 * in.sh, r1 = base + (int64_t)y1 * in.sh;
+  const int c0 = x0 * in.sw, c1 = x1 * in.sw;
+  const float a = join_bf16(in.hi[r0 + c0], in.lo[r0 + c0]);
+  const float b = join_bf16(in.hi[r0 + c1], in.lo[r0 + c1]);
+  const float c = join_bf16(in.hi[r1 + c0], in.lo[r1 + c0]);
+  const float d = join_bf16(in.hi[r1 + c1], in.lo[r1 + c1]);
+  const float y = hy * (hx * a + lx * b) + ly * (hx * c + lx * d);
+  bf16 h, l;
+  split_bf16(y, h, l);
+  const int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  st256(out.hi + oo, make_uint4((uint32_t)__bfloat16_as_ushort(h), 0, 0, 0), z);
+  st256(out.lo + oo, make_uint4((uint32_t)__bfloat16_as_ushort(l), 0, 0, 0), z);
+}
+
+cudaError_t launch_upsample2x_c1(ActView in, ActView out, cudaStream_t stream) {
+  if ((int64_t)out.N * out.H * out.W == 0) return cudaSuccess;
+  if (out.C != 16 || out.sw % 16 || ((reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo)) & 31))
+    return cudaErrorInvalidValue;
+  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
+  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  dim3 grid((unsigned)ceil_div(out.W, 256), (unsigned)(out.N * out.H));
+  upsample2x_c1_kernel<<<grid, 256, 0, stream>>>(in, out, sh, sw);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void pool_freq_mean_kernel(ActView in, ActView out) {
   const int chunks = in.C >> 3;

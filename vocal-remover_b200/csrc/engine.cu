@@ -578,7 +578,7 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
     // reads cat1 = [e1 | up(lstm)] by TMA and produces up(h) itself from d2
     ++launches;
     const ActView lstm_full = P.lstm_own ? P.lstm_up.all(N) : P.cat1.view(N, 0, H, P.lstm_coff, 16);
-    if (!timed("lstm.upsample2x", N, H, P.W, sl, [&] { return ck(launch_upsample2x(P.lstm_lo.all(N), lstm_full, sl), "lstm upsample"); }))
+    if (!timed("lstm.upsample2x", N, H, P.W, sl, [&] { return ck(launch_upsample2x_c1(P.lstm_lo.all(N), lstm_full, sl), "lstm upsample"); }))
       return false;
     if (overlap) {
       if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join") || !ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join"))

@@ -19,6 +19,8 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 cudaError_t launch_nchw_to_act(const float* x, int C, ActView dst, cudaStream_t stream);
 cudaError_t launch_act_to_nchw(ActView src, int C, float* y, cudaStream_t stream);
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream);
+// channel 0 of `in` -> channel 0 of the 16-channel group `out` (channels 1..15 written as zeros)
+cudaError_t launch_upsample2x_c1(ActView in, ActView out, cudaStream_t stream);
 cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream);
 cudaError_t launch_broadcast_rows(ActView in, ActView out, cudaStream_t stream);
 
