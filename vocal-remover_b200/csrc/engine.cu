@@ -67,6 +67,8 @@ Engine::Engine(const Config& cfg) : cfg_(cfg) {
   cudaMemcpy(twiddle_, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
   cudaMemcpy(window_, win.data(), sizeof(float) * win.size(), cudaMemcpyHostToDevice);
   cudaStreamCreateWithFlags(&s_hi_, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&s_copy_, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ev_span_, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ev_lstm_fork_, cudaEventDisableTiming);
@@ -82,6 +84,8 @@ Engine::~Engine() {
   if (ws_wave_) cudaFree(ws_wave_);
   profile_enable(false);
   if (s_hi_) cudaStreamDestroy(s_hi_);
+  if (s_copy_) cudaStreamDestroy(s_copy_);
+  if (ev_span_) cudaEventDestroy(ev_span_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
   if (ev_lstm_fork_) cudaEventDestroy(ev_lstm_fork_);
@@ -671,7 +675,8 @@ bool Engine::predict_mask(const float* mag, int N, float* mask_out, int offset, 
 }
 
 bool Engine::separate_windows(const float2* spec, int64_t T, const float* norm, int pad_l, int first, int count,
-                              float* mask, int64_t mask_T, int64_t frame_shift, int accumulate, cudaStream_t s) {
+                              float* mask, int64_t mask_T, int64_t frame_shift, int accumulate, cudaStream_t s,
+                              bool final_pass) {
   if (!finalized_) {
     err = "weights not finalized";
     return false;
@@ -697,6 +702,11 @@ bool Engine::separate_windows(const float2* spec, int64_t T, const float* norm, 
     p.t_limit = mask_T; p.roi_t = r; p.accumulate = accumulate;
     ++launches;
     if (!timed("mask_out", n_now, max_bin, W, s, [&] { return ck(launch_mask_out(p, s), "mask_out"); })) return false;
+    if (final_pass && on_frames_final_) {
+      int64_t f = p.t_base0 + (int64_t)n_now * r;
+      if (f > mask_T) f = mask_T;
+      if (f > 0 && !on_frames_final_(f)) return false;
+    }
   }
   return true;
 }
@@ -718,11 +728,11 @@ bool Engine::separate(const float2* spec, int64_t T, int tta, float* mask, cudaS
   const int64_t Wpad = pad_l + T + pad_r;
   const int patches = (int)((Wpad - 2 * cfg_.offset) / r);
   if (!normaliser(spec, T, tta ? 1 : 0, ws_norm_, s)) return false;
-  if (!separate_windows(spec, T, ws_norm_, pad_l, 0, patches, mask, T, 0, 0, s)) return false;
+  if (!separate_windows(spec, T, ws_norm_, pad_l, 0, patches, mask, T, 0, 0, s, !tta)) return false;
   if (tta) {
     const int64_t Wpad2 = Wpad + r;   // pad_l += roi/2, pad_r += roi/2 (inference.py:91-92)
     const int patches2 = (int)((Wpad2 - 2 * cfg_.offset) / r);
-    if (!separate_windows(spec, T, ws_norm_, pad_l + r / 2, 0, patches2, mask, T, r / 2, 1, s)) return false;
+    if (!separate_windows(spec, T, ws_norm_, pad_l + r / 2, 0, patches2, mask, T, r / 2, 1, s, true)) return false;
   }
   return true;
 }
@@ -853,10 +863,41 @@ bool Engine::separate_wave_host(const float* wave, int64_t L, int tta, float* in
   float* d_inst = ws_wave_ + 2 * L;
   float* d_voc = d_inst + 2 * Lo;
   if (!ck(cudaMemcpyAsync(d_in, wave, sizeof(float) * 2 * L, cudaMemcpyHostToDevice, s), "H2D wave")) return false;
-  if (!separate_wave(d_in, L, tta, d_inst, d_voc, s)) return false;
-  if (!ck(cudaMemcpyAsync(inst, d_inst, sizeof(float) * 2 * Lo, cudaMemcpyDeviceToHost, s), "D2H inst")) return false;
-  if (!ck(cudaMemcpyAsync(voc, d_voc, sizeof(float) * 2 * Lo, cudaMemcpyDeviceToHost, s), "D2H voc")) return false;
-  return ck(cudaStreamSynchronize(s), "separate_wave_host sync");
+  // The stems leave the device span by span: as soon as a window batch of the last pass has written its mask frames,
+  // the masked inverse STFT of the hops they complete runs on `s` and their device-to-host copy on the copy stream,
+  // overlapped with the next batch of the net (the copies of a 4-minute track are 169 MB).
+  if (!ensure_ws(T)) return false;
+  if (!stft(d_in, L, ws_spec_, T, nullptr, s)) return false;
+  int64_t k_done = 0;
+  bool ok = true;
+  auto flush = [&](int64_t f) -> bool {
+    // output hop k needs mask frames k and k+1
+    int64_t k1 = f >= T ? T - 1 : f - 1;
+    if (k1 <= k_done) return true;
+    if (!istft_range(ws_spec_, ws_mask_, T, k_done, k1, d_inst, d_voc, s)) return false;
+    if (!ck(cudaEventRecord(ev_span_, s), "span event") || !ck(cudaStreamWaitEvent(s_copy_, ev_span_, 0), "span wait"))
+      return false;
+    const size_t off = (size_t)cfg_.hop * (size_t)k_done, cnt = (size_t)cfg_.hop * (size_t)(k1 - k_done);
+    for (int c = 0; c < 2; ++c) {
+      if (!ck(cudaMemcpyAsync(inst + (size_t)c * Lo + off, d_inst + (size_t)c * Lo + off, sizeof(float) * cnt,
+                              cudaMemcpyDeviceToHost, s_copy_), "D2H inst") ||
+          !ck(cudaMemcpyAsync(voc + (size_t)c * Lo + off, d_voc + (size_t)c * Lo + off, sizeof(float) * cnt,
+                              cudaMemcpyDeviceToHost, s_copy_), "D2H voc"))
+        return false;
+    }
+    k_done = k1;
+    return true;
+  };
+  on_frames_final_ = flush;
+  ok = separate(ws_spec_, T, tta, ws_mask_, s);
+  on_frames_final_ = nullptr;
+  if (ok) ok = flush(T);
+  if (!ok) {
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(s_copy_);
+    return false;
+  }
+  return ck(cudaStreamSynchronize(s), "separate_wave_host sync") && ck(cudaStreamSynchronize(s_copy_), "separate_wave_host copy sync");
 }
 
 // ---------------------------------------------------------------------------------------------

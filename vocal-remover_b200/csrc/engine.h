@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -114,7 +115,8 @@ class Engine {
   bool predict_mask(const float* mag, int N, float* mask_out, int offset, cudaStream_t s);
   // windows [first, first+count) of the padded spectrogram -> mask frames; see include/vr_b200.h
   bool separate_windows(const float2* spec, int64_t T, const float* norm, int pad_l, int first, int count,
-                        float* mask, int64_t mask_T, int64_t frame_shift, int accumulate, cudaStream_t s);
+                        float* mask, int64_t mask_T, int64_t frame_shift, int accumulate, cudaStream_t s,
+                        bool final_pass = false);
   bool separate(const float2* spec, int64_t T, int tta, float* mask, cudaStream_t s);
   bool apply_mask(const float2* spec, const float* mask, int64_t T, float2* y, float2* v, cudaStream_t s);
   bool separate_wave(const float* wave, int64_t L, int tta, float* inst, float* voc, cudaStream_t s);
@@ -173,6 +175,10 @@ class Engine {
   // the high-band BaseNets of stages 1-2 run on their own stream next to the low-band chain (independent until
   // stage 3, lib/nets.py:88-99); disabled while per-kernel profiling is on so event timings stay per-kernel
   cudaStream_t s_hi_ = nullptr;
+  // host-buffer entry: finished output spans are copied back on their own stream while the next window batch computes
+  cudaStream_t s_copy_ = nullptr;
+  cudaEvent_t ev_span_ = nullptr;
+  std::function<bool(int64_t)> on_frames_final_;   // called after a batch of the last pass: mask frames [0, f) are final
   cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_lstm_fork_ = nullptr, ev_lstm_join_ = nullptr;
 
   float2* twiddle_ = nullptr;
