@@ -42,10 +42,11 @@ UNIT = 'audio-s/s'
 SR = 44100
 SECONDS_PER_GPU = 240.0
 CONV_FLOP_PER_WINDOW = 135.714e9
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the tensor-core convolution launches of four 11-window
-# passes, / 44 (ncu capture profiles/r01_launches_bench30s_fused.csv, decoder upsample fused into dec1/dec2; the build
-# before that fusion moved 1.225 GB); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
-CONV_DRAM_BYTES_PER_WINDOW = 0.879e9
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the tensor-core convolution launches of the round-2 ncu launch
+# list (profiles/r02_launches_bench.csv: 128.9 GB over the 141 windows that bench run pushes through the net; round 1
+# measured 0.879 GB with the LSTM channel still interleaved into the skip tensor, 1.225 GB before the decoder upsample
+# was fused); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
+CONV_DRAM_BYTES_PER_WINDOW = 0.914e9
 GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'ref_10s_default.npz')
 
 
@@ -361,6 +362,7 @@ def run_gpu(args):
 
     tta_steps = max(1, min(args.steps, 3))
     step_tta()
+    step_tta()
     tta_ms = timed(step_tta, tta_steps) / tta_steps
 
     # ---- BASELINE configs[4]: a fixed 40-minute stream on the N GPUs of this run (strong scaling) ----
@@ -374,7 +376,8 @@ def run_gpu(args):
         def step_long():
             return vr_dist.separate_wave(sp, d_long, tta=False, world=world, rank=rank)
 
-        step_long()
+        step_long()   # two warm-up calls: the multi-GPU path alternates between two sets of shared stem buffers,
+        step_long()   # each allocated (and IPC-mapped) on its first use
         long_steps = 2
         long_ms = timed(step_long, long_steps) / long_steps
         strong = {'value': 2400.0 / (long_ms * 1e-3), 'unit': UNIT, 'ms_per_step': long_ms, 'steps': long_steps,
@@ -426,8 +429,8 @@ def run_gpu(args):
                           'bf16x3 split precision)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                 'traffic': CONV_DRAM_BYTES_PER_WINDOW * n_windows / world / max(1.0, tc_n),
-                'traffic_note': 'average DRAM bytes per convolution launch = 0.879 GB per window (ncu, '
-                                'profiles/r01_launches_bench30s_fused.csv) x windows per rank / launches',
+                'traffic_note': 'average DRAM bytes per convolution launch = 0.914 GB per window (ncu, '
+                                'profiles/r02_launches_bench.csv) x windows per rank / launches',
                 'peak_source': peak_src,
                 'note': 'achieved = algorithmic conv FLOPs (real channel counts, 1x per product; the kernel issues 3 '
                         'bf16 MMA passes per product) of %d launches / their summed CUDA-event time %.2f ms on rank '

@@ -23,7 +23,7 @@ tot = sum(a['gpu__time_duration.sum'] for a in agg.values())
 conv = 0.0
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['gpu__time_duration.sum']):
     dram = a['dram__bytes_read.sum'] + a['dram__bytes_write.sum']
-    if k.startswith('conv_tc'):
+    if 'conv_tc' in k:
         conv += dram
     print('%-40s n=%4d t=%9.1f us share=%.3f dram=%.3f GB' % (k[:40], len(ids[k]), a['gpu__time_duration.sum'],
                                                              a['gpu__time_duration.sum'] / tot, dram / 1e9))

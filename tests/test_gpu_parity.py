@@ -382,3 +382,23 @@ def test_silent_track_does_not_poison_the_context(default_model, wave10, golden_
     after, _ = sp.separate_wave(wave10)
     assert np.isfinite(after).all()
     assert np.array_equal(before, after)
+
+
+def test_pseudo_instruments_vs_oracle(default_model):
+    """pseudo.py:56-71 (second caller of Separator.separate_tta): STFT of both tracks, separate_tta(X - y), y + a_spec,
+    device-resident in PseudoLabeler, against the CPU oracle of the same steps."""
+    import pseudo
+    from lib import synth
+    from oracle import separator_oracle, stft_oracle
+    X = synth.sine_mix(5.0)
+    y = (0.6 * X + 0.1 * synth.sine_mix(5.0, seed=3)).astype(np.float32)
+    got = pseudo.PseudoLabeler(default_model, _dev(), 4, 256, False).pseudo_instruments(X, y)
+    Xs = stft_oracle.wave_to_spectrogram(X, 1024, 2048)
+    ys = stft_oracle.wave_to_spectrogram(y, 1024, 2048)
+    sd = synth.to_torch_state_dict(synth.make_state_dict())
+    a_spec, _ = separator_oracle.separate(sd, Xs - ys, tta=True)
+    ref = ys + a_spec
+    assert got.shape == ref.shape and got.dtype == np.complex64
+    err = np.abs(got - ref).max() / np.abs(Xs - ys).max()
+    record_parity('pseudo_instruments_5s_normalised_vs_oracle', err, MASK_TOL)
+    assert err < MASK_TOL

@@ -220,3 +220,41 @@ def test_sharded_tta_plan_reproduces_the_unsharded_combine(T, world):
         assert np.array_equal(local[:, f0:f1], ref[:, f0:f1])
         covered[f0:f1] = True
     assert covered.all()
+
+
+def test_make_pair_and_file_sharding(tmp_path):
+    """lib/dataset.py:144-160 (pairing by sorted order, audio extensions only) and the file-level sharding of pseudo.py."""
+    from lib import dataset
+    mix, inst = tmp_path / 'mix', tmp_path / 'inst'
+    mix.mkdir()
+    inst.mkdir()
+    for name in ('b.wav', 'a.flac', 'c.mp3', 'notes.txt'):
+        (mix / name).write_bytes(b'')
+    for name in ('2.wav', '1.wav', '3.wav', 'cover.jpg'):
+        (inst / name).write_bytes(b'')
+    pairs = dataset.make_pair(str(mix), str(inst))
+    assert [(os.path.basename(a), os.path.basename(b)) for a, b in pairs] == [('a.flac', '1.wav'), ('b.wav', '2.wav'),
+                                                                               ('c.mp3', '3.wav')]
+    files = list(range(11))
+    shards = [dataset.shard_files(files, 4, r) for r in range(4)]
+    assert sorted(sum(shards, [])) == files                       # every file exactly once
+    assert max(len(x) for x in shards) - min(len(x) for x in shards) <= 1
+    assert dataset.shard_files(files, 1, 0) == files
+
+
+def test_align_wave_head_and_tail_recovers_a_known_delay():
+    """lib/spec_utils.py:96-119 restated (trim + cross-correlation of the first four seconds): a delayed, silence-padded
+    copy must come out sample-aligned and of equal length."""
+    from lib import spec_utils
+    sr = 8000
+    rng = np.random.default_rng(1)
+    core = (rng.standard_normal((2, sr * 5)) * 0.3).astype(np.float32)
+    a = np.concatenate([np.zeros((2, 3000), np.float32), core, np.zeros((2, 2000), np.float32)], axis=1)
+    b = np.concatenate([np.zeros((2, 1200), np.float32), 0.7 * core[:, 137:], np.zeros((2, 4000), np.float32)], axis=1)
+    a2, b2 = spec_utils.align_wave_head_and_tail(a, b, sr)
+    assert a2.shape == b2.shape and a2.shape[1] > sr * 4
+    # sample-aligned: in the interior (away from the frame-granular trim edges) b2 is exactly 0.7 * a2
+    mid = slice(sr, 3 * sr)
+    assert np.abs(b2[:, mid] - 0.7 * a2[:, mid]).max() < 1e-6
+    t, (s0, s1) = spec_utils._trim_silence(a)
+    assert s0 <= 3000 and s0 >= 3000 - 2048 and s1 >= 3000 + sr * 5 and t.shape[1] == s1 - s0

@@ -479,6 +479,15 @@ bool Engine::run_conv(ConvLayer& L, const ActView& in, const ActView& out, cudaS
                       const ActView* extra) {
   ++launches;
   const bool use_tc = L.tc && cfg_.conv_mode == 0 && tc_supported(L, in, out);
+  if (!use_tc && cfg_.conv_mode == 0 && L.Cout >= 4 && !warned_simt_) {
+    // loud, once per context: this geometry does not tile for the tcgen05 kernels (e.g. a cropsize whose feature-map
+    // widths are not powers of two / multiples of 128) and runs on the fp32 CUDA-core kernel, an order of magnitude slower
+    warned_simt_ = true;
+    fprintf(stderr,
+            "libvr_b200: WARNING: %s (N=%d, %dx%d -> %dx%d) does not tile for the tensor-core kernels and runs on the "
+            "CUDA-core convolution; use a cropsize whose maps tile (e.g. 256) for full speed\n",
+            L.name.c_str(), in.N, in.H, in.W, out.H, out.W);
+  }
   // algorithmic FLOPs with the real (un-padded) channel counts: 2 * pixels * Cout * Cin * taps
   const int pi = prof_begin(up_src ? L.name + "+up" : L.name, use_tc ? 1 : 0,
                             2.0 * (double)out.N * out.H * out.W * L.Cout * L.Cin * L.k * L.k, out.N, out.H, out.W, s);

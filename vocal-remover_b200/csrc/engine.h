@@ -146,6 +146,7 @@ class Engine {
  private:
   Config cfg_;
   bool finalized_ = false;
+  bool warned_simt_ = false;   // the CUDA-core fallback warning was printed
   std::map<std::string, HostTensor> sd_;
   std::vector<void*> allocs_;
   int last_n_ = 0;

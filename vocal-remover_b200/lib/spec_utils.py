@@ -121,3 +121,53 @@ def merge_artifacts(y_mask, thres=0.05, min_range=64, fade_size=32):
     weight = artifact_weights(y_mask.min(axis=(0, 1)), thres, min_range, fade_size)
     y_mask += weight[None, None, :] * (1 - y_mask)
     return y_mask
+
+
+def _trim_silence(y, top_db=60, frame_length=2048, hop_length=512):
+    """Restatement of ``librosa.effects.trim(y)`` (librosa 0.10 defaults; librosa is absent offline: parity unpinned like
+    the STFT): frame RMS (centred frames, zero padding) -> dB relative to the maximum -> first / last frame above
+    -top_db, per channel with the maximum taken across channels.  Returns (trimmed, (start, end))."""
+    y = np.asarray(y)
+    L = y.shape[-1]
+    yp = np.pad(y.reshape(-1, L).astype(np.float64), ((0, 0), (frame_length // 2, frame_length // 2)))
+    n_frames = 1 + (yp.shape[1] - frame_length) // hop_length
+    csum = np.concatenate([np.zeros((yp.shape[0], 1)), np.cumsum(yp ** 2, axis=1)], axis=1)
+    starts = np.arange(n_frames) * hop_length
+    power = (csum[:, starts + frame_length] - csum[:, starts]) / frame_length
+    rms = np.sqrt(np.maximum(power, 0.0))
+    ref = rms.max()
+    db = 20.0 * np.log10(np.maximum(1e-5, rms)) - 20.0 * np.log10(np.maximum(1e-5, ref))
+    non_silent = (db > -top_db).max(axis=0)
+    nz = np.flatnonzero(non_silent)
+    if nz.size == 0:
+        return y[..., 0:0], (0, 0)
+    start = int(nz[0]) * hop_length
+    end = min(L, (int(nz[-1]) + 1) * hop_length)
+    return y[..., start:end], (start, end)
+
+
+def align_wave_head_and_tail(a, b, sr):
+    """lib/spec_utils.py:96-119: trim both tracks, estimate their delay from the cross-correlation of the first four
+    seconds (mono sums, mean removed) and crop them to the common aligned span."""
+    a, _ = _trim_silence(a)
+    b, _ = _trim_silence(b)
+    a_mono = a[:, :sr * 4].sum(axis=0)
+    b_mono = b[:, :sr * 4].sum(axis=0)
+    a_mono = a_mono - a_mono.mean()
+    b_mono = b_mono - b_mono.mean()
+    offset = len(a_mono) - 1
+    # np.correlate(a, b, 'full') through the FFT (the direct form is O(n^2) on 4 s of audio)
+    n = len(a_mono) + len(b_mono) - 1
+    nfft = 1 << (n - 1).bit_length()
+    corr = np.fft.irfft(np.fft.rfft(a_mono, nfft) * np.conj(np.fft.rfft(b_mono, nfft)), nfft)
+    corr = np.concatenate([corr[nfft - (len(b_mono) - 1):], corr[:len(a_mono)]])
+    delay = int(np.argmax(corr)) - offset   # as the reference: offset = len(a_mono) - 1
+    if delay > 0:
+        a = a[:, delay:]
+    else:
+        b = b[:, np.abs(delay):]
+    if a.shape[1] < b.shape[1]:
+        b = b[:, :a.shape[1]]
+    else:
+        a = a[:, :b.shape[1]]
+    return a, b
