@@ -307,6 +307,11 @@ def test_full_size_track_properties(default_model):
     sp5 = inference.Separator(default_model, _dev(), 5, 256, False)
     inst5, _ = sp5.separate_wave(d_wave)
     assert (inst - inst5).abs().max().item() < 1e-5
+    # ... and neither must one batch holding the whole track (81 windows x 1024 rows exceeds 65535 grid rows)
+    sp81 = inference.Separator(default_model, _dev(), 81, 256, False)
+    inst81, _ = sp81.separate_wave(d_wave)
+    assert (inst - inst81).abs().max().item() < 1e-5
+    del sp81, sp5
     # the first 10 s see the same windows as the 10 s golden case except for the global normaliser, which is
     # identical here (same sine mix amplitude): compare the first two windows' worth of samples with the oracle
     assert torch.isfinite(inst).all() and torch.isfinite(voc).all()

@@ -92,6 +92,10 @@ struct RowsParams {
                   // one producer per ring (two producers sharing one ring can lap each other: the 1-bit phase
                   // parity cannot tell 'two uses behind' from 'up to date')
   float up_sh, up_sw;
+  // fused 1x1 convolution to ONE channel (the LSTM branch's input convolution, lib/layers.py:112,126): every output pixel
+  // adds sum_c dot_w[c] * y[c] over this tile's output channels to dot_out[(n * H + h) * W + w] (pre-zeroed fp32 plane)
+  const float* dot_w;
+  float* dot_out;
 };
 
 // 8-channel groups of chunk cc that carry any non-zero weight (4 bits per 32-channel chunk)
@@ -175,6 +179,20 @@ __device__ __forceinline__ void issue_row_fresh_head(uint32_t d, uint32_t a_hi, 
   }
 }
 
+// sum_i w[co + i] * act(v[i] + bias[co + i]) over CNT accumulator columns: the fused single-channel 1x1 convolution on
+// the fp32 activations of this tile (weights past Cout are zero)
+template <int CNT>
+__device__ __forceinline__ float dot_activated(const float* v, const float* bias_s, const float* dot_s, int co, float slope) {
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CNT; i += 2) {
+    const float t0 = v[i] + bias_s[co + i], t1 = v[i + 1] + bias_s[co + i + 1];
+    d0 = fmaf(fmaxf(t0, 0.f) + slope * fminf(t0, 0.f), dot_s[co + i], d0);
+    d1 = fmaf(fmaxf(t1, 0.f) + slope * fminf(t1, 0.f), dot_s[co + i + 1], d1);
+  }
+  return d0 + d1;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kRowsThreads, 1)
     conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -190,6 +208,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float bias_s[256];   // folded-BN bias of every N tile, staged once (a global load per use stalled the epilogue)
+  __shared__ float dot_s[256];    // weights of the fused single-channel 1x1 convolution (zeros past Cout)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,7 +242,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n_tiles * BN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
+  for (int i = threadIdx.x; i < p.n_tiles * BN; i += blockDim.x) {
+    bias_s[i] = __ldg(p.bias + i);
+    dot_s[i] = p.dot_out && i < p.Cout ? __ldg(p.dot_w + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -601,6 +623,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
           }
+          if (p.dot_out) {
+            const float d = dot_activated<32>(v, bias_s, dot_s, nt * BN, slope) +
+                            dot_activated<32>(v2, bias_s, dot_s, nt * BN + 32, slope);
+            atomicAdd(p.dot_out + ((int64_t)n * p.H + (h0 + orow)) * p.W + (w0 + px), d);
+          }
           epilogue_store<2>(v, bias_s, nt * BN, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
           epilogue_store<2>(v2, bias_s, nt * BN + 32, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
         } else {
@@ -612,6 +639,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[acc]));
           }
+          if (p.dot_out)
+            atomicAdd(p.dot_out + ((int64_t)n * p.H + (h0 + orow)) * p.W + (w0 + px),
+                      dot_activated<BN>(v, bias_s, dot_s, nt * BN, slope));
           epilogue_store<(BN >= 32 ? 2 : 1)>(v, bias_s, nt * BN, p.Cout, slope, p.out_hi + obase, p.out_lo + obase);
         }
       }
@@ -778,6 +808,7 @@ cudaError_t tc_rows_launch(ConvLayer& L, TcConv& tc, const ActView& in, const Ac
   p.x_hi = p.x_lo = nullptr; p.xsn = p.xsh = 0; p.xsw = 0;
   p.trace = g_tc_debug[0] == 1 ? 1 : 0;
   p.up_sh = p.up_sw = 0.f;
+  p.dot_w = L.dot_w; p.dot_out = L.dot_w ? L.dot_out : nullptr;
   p.a_c_off = 0;
   p.l_chunk = extra ? R.chunks - 1 : -1;
   p.kmask = g_tc_debug[6] == 1 ? R.kmask : ~0ull;   // VR_KSKIP=0 issues the all-zero-weight channel groups too

@@ -85,17 +85,17 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// One thread per (output pixel, 8-channel chunk); grid.y = (image, output row) so all per-thread index math is
-// 32-bit with one division.  Source index and weights follow ATen's upsample_bilinear2d with
+// One thread per (output pixel, 8-channel chunk); grid.x = (image, output row) - N * H can exceed the 65535 limit of
+// grid.y - so all per-thread index math is 32-bit with one division.  Source index and weights follow ATen's upsample_bilinear2d with
 // align_corners=True: scale = (in-1)/(out-1) in fp32, src = scale*dst.
 template <int CH>   // channels per thread: 8 (one 16-byte access per plane) or 16 (32 bytes: STG.256, twice the loads in flight)
 __global__ void __launch_bounds__(256) upsample2x_kernel(ActView in, ActView out, int chunks, float sh, float sw) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = blockIdx.y * blockDim.x + threadIdx.x;
   if (idx >= out.W * chunks) return;
   const int wo = idx / chunks;
   const int ck = idx - wo * chunks;
-  const int n = blockIdx.y / out.H;
-  const int ho = blockIdx.y - n * out.H;
+  const int n = blockIdx.x / out.H;
+  const int ho = blockIdx.x - n * out.H;
   const float fy = sh * ho, fx = sw * wo;
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
@@ -142,7 +142,7 @@ cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
   const bool wide = in.C % 16 == 0 && out.sw % 16 == 0 && in.sw % 16 == 0 &&
                     ((reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo)) & 31) == 0;
   const int chunks = wide ? in.C >> 4 : in.C >> 3;
-  dim3 grid((unsigned)ceil_div(out.W * chunks, 256), (unsigned)(out.N * out.H));
+  dim3 grid((unsigned)(out.N * out.H), (unsigned)ceil_div(out.W * chunks, 256));
   if (wide)
     upsample2x_kernel<16><<<grid, 256, 0, stream>>>(in, out, chunks, sh, sw);
   else
@@ -150,26 +150,22 @@ cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// Single-channel variant for the LSTM branch (lib/nets.py:38, layers.py:52): channel 0 of `in` is up-sampled with the same
-// arithmetic as upsample2x_kernel and written as channel 0 of a 16-channel group whose other channels are zeros (one full
-// 32-byte sector per plane and pixel).  The generic kernel spent its time blending the 15 zero channels.
-__global__ void __launch_bounds__(256) upsample2x_c1_kernel(ActView in, ActView out, float sh, float sw) {
-  const int wo = blockIdx.x * blockDim.x + threadIdx.x;
+// Single-channel variant for the LSTM branch (lib/nets.py:38, layers.py:52): the source is the fp32 plane in[bin][n][t] the dense GEMM wrote
+// (strides in_sn, in_sh in floats, t contiguous); the result goes to channel 0 of a 16-channel group (15 zeros).
+__global__ void __launch_bounds__(256) upsample2x_c1_kernel(const float* __restrict__ in, int inH, int inW, int64_t in_sn,
+                                                            int64_t in_sh, ActView out, float sh, float sw) {
+  const int wo = blockIdx.y * blockDim.x + threadIdx.x;   // rows on grid.x: N * H exceeds the 65535 limit of grid.y
   if (wo >= out.W) return;
-  const int n = blockIdx.y / out.H;
-  const int ho = blockIdx.y - n * out.H;
+  const int n = blockIdx.x / out.H;
+  const int ho = blockIdx.x - n * out.H;
   const float fy = sh * ho, fx = sw * wo;
   const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = y0 + (y0 < in.H - 1 ? 1 : 0), x1 = x0 + (x0 < in.W - 1 ? 1 : 0);
+  const int y1 = y0 + (y0 < inH - 1 ? 1 : 0), x1 = x0 + (x0 < inW - 1 ? 1 : 0);
   const float ly = fy - y0, lx = fx - x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const int64_t base = (int64_t)n * in.sn;
-  const int64_t r0 = base + (int64_t)y0 * in.sh, r1 = base + (int64_t)y1 * in.sh;
-  const int c0 = x0 * in.sw, c1 = x1 * in.sw;
-  const float a = join_bf16(in.hi[r0 + c0], in.lo[r0 + c0]);
-  const float b = join_bf16(in.hi[r0 + c1], in.lo[r0 + c1]);
-  const float c = join_bf16(in.hi[r1 + c0], in.lo[r1 + c0]);
-  const float d = join_bf16(in.hi[r1 + c1], in.lo[r1 + c1]);
+  const float* r0 = in + (int64_t)n * in_sn + (int64_t)y0 * in_sh;
+  const float* r1 = in + (int64_t)n * in_sn + (int64_t)y1 * in_sh;
+  const float a = __ldg(r0 + x0), b = __ldg(r0 + x1), c = __ldg(r1 + x0), d = __ldg(r1 + x1);
   const float y = hy * (hx * a + lx * b) + ly * (hx * c + lx * d);
   bf16 h, l;
   split_bf16(y, h, l);
@@ -179,14 +175,15 @@ __global__ void __launch_bounds__(256) upsample2x_c1_kernel(ActView in, ActView 
   st256(out.lo + oo, make_uint4((uint32_t)__bfloat16_as_ushort(l), 0, 0, 0), z);
 }
 
-cudaError_t launch_upsample2x_c1(ActView in, ActView out, cudaStream_t stream) {
+cudaError_t launch_upsample2x_c1(const float* in, int inH, int inW, int64_t in_sn, int64_t in_sh, ActView out,
+                                 cudaStream_t stream) {
   if ((int64_t)out.N * out.H * out.W == 0) return cudaSuccess;
   if (out.C != 16 || out.sw % 16 || ((reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo)) & 31))
     return cudaErrorInvalidValue;
-  const float sh = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
-  const float sw = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
-  dim3 grid((unsigned)ceil_div(out.W, 256), (unsigned)(out.N * out.H));
-  upsample2x_c1_kernel<<<grid, 256, 0, stream>>>(in, out, sh, sw);
+  const float sh = out.H > 1 ? (float)(inH - 1) / (float)(out.H - 1) : 0.f;
+  const float sw = out.W > 1 ? (float)(inW - 1) / (float)(out.W - 1) : 0.f;
+  dim3 grid((unsigned)(out.N * out.H), (unsigned)ceil_div(out.W, 256));
+  upsample2x_c1_kernel<<<grid, 256, 0, stream>>>(in, inH, inW, in_sn, in_sh, out, sh, sw);
   return cudaGetLastError();
 }
 

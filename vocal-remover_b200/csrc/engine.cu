@@ -212,7 +212,6 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.e1_coff = P.skip_only ? 0 : P.e1_off;           // position of e1 in the cat1 buffer
   P.lstm_coff = !P.skip_only ? 2 * n : P.lstm_own ? 0 : n;
   P.cat1 = make_buffer(Nb, H, W, !P.skip_only ? c1 : P.lstm_own ? n : round_up(n + lg, 32));
-  if (P.skip_only) P.lstm_lo = make_buffer(Nb, H / 2, W / 2, lg);
   if (P.lstm_own) P.lstm_up = make_buffer(Nb, H, W, lg);
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
@@ -265,6 +264,8 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
     for (int i = 0; i < 2 * n; ++i) perm[(size_t)i] = i;
     perm[(size_t)(!P.skip_only ? 2 * n : P.lstm_own ? 2 * n + round_up(n, 32) : 2 * n + n)] = 2 * n;
     for (int i = 0; i < n; ++i) perm[(size_t)(P.e1_off + i)] = 2 * n + 1 + i;
+    // (the 64-wide tile was measured on dec1 as well - one N tile instead of two for n = 64 - and is no faster there:
+    //  with its single accumulator set the epilogue no longer overlaps the next tile's products)
     if (!make_conv(P.dec[3], prefix + ".dec1.conv1", perm, c1, 3, 1, 1, 1, ACT_RELU)) return false;
   }
 
@@ -320,26 +321,26 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
         !need(lp + ".dense.1.running_mean", {Q.bins}, &m1) || !need(lp + ".dense.1.running_var", {Q.bins}, &v1) ||
         !need(lp + ".dense.1.num_batches_tracked", {}, &c1t))
       return false;
-    std::vector<float> wdT((size_t)K * Q.bins), sc((size_t)Q.bins), sh((size_t)Q.bins);
+    std::vector<float> sc((size_t)Q.bins), sh((size_t)Q.bins);
     for (int bin = 0; bin < Q.bins; ++bin) {
       const double s = (double)g1->data[(size_t)bin] / sqrt((double)v1->data[(size_t)bin] + kBnEps);
       sc[(size_t)bin] = (float)s;
       sh[(size_t)bin] = (float)(s * ((double)db->data[(size_t)bin] - (double)m1->data[(size_t)bin]) +
                                 (double)b1->data[(size_t)bin]);
-      for (int k = 0; k < K; ++k) wdT[(size_t)k * Q.bins + bin] = dw->data[(size_t)bin * K + k];
     }
-    Q.wdT = (float*)dalloc(sizeof(float) * wdT.size());
+    Q.wd = (float*)dalloc(sizeof(float) * dw->data.size());
     Q.dscale = (float*)dalloc(sizeof(float) * sc.size());
     Q.dshift = (float*)dalloc(sizeof(float) * sh.size());
-    if (!Q.wdT || !Q.dscale || !Q.dshift) return false;
-    cudaMemcpy(Q.wdT, wdT.data(), sizeof(float) * wdT.size(), cudaMemcpyHostToDevice);
+    if (!Q.wd || !Q.dscale || !Q.dshift) return false;
+    cudaMemcpy(Q.wd, dw->data.data(), sizeof(float) * dw->data.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(Q.dscale, sc.data(), sizeof(float) * sc.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(Q.dshift, sh.data(), sizeof(float) * sh.size(), cudaMemcpyHostToDevice);
   }
   Q.l0 = (float*)dalloc(sizeof(float) * (size_t)Nb * Q.T * Q.bins);
   Q.xp = (float*)dalloc(sizeof(float) * (size_t)Nb * Q.T * 8 * Q.hid);
   Q.hs = (float*)dalloc(sizeof(float) * (size_t)Nb * Q.T * 2 * Q.hid);
-  return Q.l0 && Q.xp && Q.hs;
+  Q.y = (float*)dalloc(sizeof(float) * (size_t)Nb * Q.T * Q.bins);
+  return Q.l0 && Q.xp && Q.hs && Q.y;
 }
 
 bool Engine::finalize() {
@@ -563,35 +564,50 @@ bool Engine::run_basenet(BaseNetPlan& P, const ActView& in, const ActView& out, 
   if (!timed("upsample2x", N, H / 4, P.W / 4, s, [&] { return ck(launch_upsample2x(P.d4.all(N), P.cat3.view(N, 0, H / 4, 0, 6 * n), s), "up3"); }))
     return false;
   if (!run_conv(P.dec[1], P.cat3.all(N), P.d3.all(N), s)) return false;
-  if (!run_decoder(P.dec[2], P.d3.all(N), P.cat2, N, P.d2.view(N, 0, H / 2, 0, 2 * n), s)) return false;
+  // The LSTM branch's 1x1 input convolution (2n -> 1, lib/layers.py:112,126) is one dot product per pixel of dec2's
+  // output: the row kernel's epilogue accumulates it from the fp32 activations it is about to store.
+  LstmPlan& Q = P.lstm;
+  const ActView d2v = P.d2.view(N, 0, H / 2, 0, 2 * n);
+  const bool dot_fused = cfg_.conv_mode == 0 && P.dec[2].tc && tc_supported(P.dec[2], P.cat2.all(N), d2v) &&
+                         tc_rows_supported(P.dec[2], *P.dec[2].tc, P.cat2.all(N), d2v);
+  if (dot_fused) {
+    if (!ck(cudaMemsetAsync(Q.l0, 0, sizeof(float) * (size_t)N * Q.bins * Q.T, s), "lstm conv clear")) return false;
+    P.dec[2].dot_w = Q.conv_w;
+    P.dec[2].dot_out = Q.l0;
+  }
+  const bool dec2_ok = run_decoder(P.dec[2], P.d3.all(N), P.cat2, N, d2v, s);
+  P.dec[2].dot_w = nullptr;
+  P.dec[2].dot_out = nullptr;
+  if (!dec2_ok) return false;
   // LSTM branch -> channel 2n of d2 (lib/nets.py:38, lib/layers.py:124-133).  Its 128-step recurrence keeps only
   // 2N CTAs busy, so when a side stream is free (stage 3) it runs there while the main stream upsamples the 2n
   // convolution channels of d2; only the LSTM channel's 16-channel group is upsampled after the join.
-  LstmPlan& Q = P.lstm;
   const bool overlap = side != nullptr && !profiling_;
   cudaStream_t sl = overlap ? side : s;
   if (overlap) {
     if (!ck(cudaEventRecord(ev_lstm_fork_, s), "lstm fork") || !ck(cudaStreamWaitEvent(side, ev_lstm_fork_, 0), "lstm fork"))
       return false;
   }
-  launches += 5;
-  if (!timed("lstm.inconv", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_inconv(P.d2.view(N, 0, H / 2, 0, 2 * n), Q.conv_w, Q.conv_bias, Q.l0, sl), "lstm conv"); }))
+  launches += dot_fused ? 3 : 4;
+  if (!dot_fused &&
+      !timed("lstm.inconv", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_inconv(d2v, Q.conv_w, Q.l0, sl), "lstm conv"); }))
     return false;
-  if (!timed("lstm.input_projection", N, H / 2, P.W / 2, sl, [&] { return ck(launch_gemm_nt(Q.l0, Q.wih, Q.bih, Q.xp, N * Q.T, 8 * Q.hid, Q.bins, sl), "lstm input projection"); }))
+  if (!timed("lstm.input_projection", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_input_projection(Q.l0, Q.conv_bias, Q.wih, Q.bih, Q.xp, N, Q.T, Q.bins, 8 * Q.hid, sl), "lstm input projection"); }))
     return false;
   if (!timed("lstm.recurrence", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_recurrence(Q.xp, Q.whh, Q.hs, N, Q.T, Q.hid, sl), "lstm recurrence"); }))
     return false;
-  // the LSTM channel at half resolution: channel 2n of d2 (staged layout) or channel 0 of lstm_lo (fused layout)
-  const ActView lstm_dst = P.skip_only ? P.lstm_lo.all(N) : P.d2.all(N);
-  const int lstm_ch = P.skip_only ? 0 : 2 * n;
-  if (!timed("lstm.dense", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_dense(Q.hs, Q.wdT, Q.dscale, Q.dshift, N, Q.T, 2 * Q.hid, Q.bins, lstm_dst, lstm_ch, sl), "lstm dense"); }))
+  // the branch output at half resolution: fp32 plane y[bin][n][t]
+  if (!timed("lstm.dense", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_dense(Q.hs, Q.wd, Q.dscale, Q.dshift, N * Q.T, 2 * Q.hid, Q.bins, Q.y, sl), "lstm dense"); }))
+    return false;
+  ++launches;
+  if (!P.skip_only &&   // staged layout: it becomes channel 2n of d2 and is up-sampled together with h
+      !timed("lstm.to_channel", N, H / 2, P.W / 2, sl, [&] { return ck(launch_lstm_plane_to_channel(Q.y, N, Q.T, Q.bins, P.d2.all(N), 2 * n, sl), "lstm channel"); }))
     return false;
   if (P.skip_only) {
-    // fused layout: up(lstm) -> its 8-channel group of cat1 (small kernel on the LSTM's stream), then the row kernel
-    // reads cat1 = [e1 | up(lstm)] by TMA and produces up(h) itself from d2
-    ++launches;
+    // fused layout: up(lstm) -> its 16-channel group of cat1 / lstm_up (small kernel on the LSTM's stream), then the row
+    // kernel reads [e1 | up(lstm)] by TMA and produces up(h) itself from d2
     const ActView lstm_full = P.lstm_own ? P.lstm_up.all(N) : P.cat1.view(N, 0, H, P.lstm_coff, 16);
-    if (!timed("lstm.upsample2x", N, H, P.W, sl, [&] { return ck(launch_upsample2x_c1(P.lstm_lo.all(N), lstm_full, sl), "lstm upsample"); }))
+    if (!timed("lstm.upsample2x", N, H, P.W, sl, [&] { return ck(launch_upsample2x_c1(Q.y, Q.bins, Q.T, Q.T, (int64_t)N * Q.T, lstm_full, sl), "lstm upsample"); }))
       return false;
     if (overlap) {
       if (!ck(cudaEventRecord(ev_lstm_join_, side), "lstm join") || !ck(cudaStreamWaitEvent(s, ev_lstm_join_, 0), "lstm join"))

@@ -50,6 +50,10 @@ struct ConvLayer {
   std::vector<float> w_host;     // packed copy kept for the tensor-core packer
   std::vector<float> bias_host;
   bool rows_wide = false;        // row kernel: 64 output channels per tile (decoder layers whose upsample is fused)
+  // set around ONE launch by the caller: the row kernel also accumulates sum_c dot_w[c] * y[c] per output pixel into the
+  // pre-zeroed plane dot_out[n][h][w] (the LSTM branch's 1x1 input convolution fused into dec2)
+  const float* dot_w = nullptr;
+  float* dot_out = nullptr;
   std::shared_ptr<TcConv> tc;    // null -> CUDA-core kernel
 };
 
@@ -60,12 +64,13 @@ struct LstmPlan {
   float* wih = nullptr;      // [8*hid][bins]  (forward rows then reverse rows)
   float* bih = nullptr;      // [8*hid]        bias_ih + bias_hh
   float* whh = nullptr;      // [2][4*hid][hid]
-  float* wdT = nullptr;      // [2*hid][bins]
+  float* wd = nullptr;       // [bins][2*hid]
   float* dscale = nullptr;   // [bins]  BatchNorm1d scale
   float* dshift = nullptr;   // [bins]  scale*linear_bias + BatchNorm1d shift
-  float* l0 = nullptr;       // [N][T][bins]
+  float* l0 = nullptr;       // [N][bins][T]  1x1 convolution, pre-activation
   float* xp = nullptr;       // [N][T][8*hid]
   float* hs = nullptr;       // [N][T][2*hid]
+  float* y = nullptr;        // [bins][N][T]  the branch output at half resolution
 };
 
 struct BaseNetPlan {
@@ -74,7 +79,7 @@ struct BaseNetPlan {
   ConvLayer enc1, enc_a[4], enc_b[4], aspp1, aspp2, aspp_d[3], bott, dec[4];   // dec[0]=dec4 .. dec[3]=dec1
   LstmPlan lstm;
   // skip_only: dec1's upsample of h is fused into the row kernel and d2 = [h 2n] only; the single LSTM channel is
-  // up-sampled by a small kernel from lstm_lo (half resolution, 16-channel group) into a 16-channel group at full
+  // up-sampled by a small kernel from lstm.y (half resolution, fp32 plane) into a 16-channel group at full
   // resolution: channels [n, n+16) of cat1 = [e1 n | up(lstm) 1 + 15 zeros] when e1 leaves room in its chunk (n = 16),
   // else the buffer lstm_up of its own (n = 32: cat1 = [e1 n] stays dense for enc2.conv1, and the row kernel reads the
   // group as its last chunk through a second tensor map).  Otherwise (CUDA-core validation mode, nets whose
@@ -83,7 +88,7 @@ struct BaseNetPlan {
   int e1_coff = 0;          // channel offset of e1 inside cat1
   int lstm_coff = 0;        // skip_only: channel offset of the up-sampled LSTM channel inside cat1 (or 0 in lstm_up)
   bool lstm_own = false;    // skip_only: the up-sampled LSTM group lives in lstm_up, not in cat1
-  Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2, lstm_lo, lstm_up;
+  Buffer cat1, t2, cat2, t3, cat3, t4, cat4, t5, e5, pool, f1, acat, ao, d4, d3, d2, lstm_up;
   int e1_off = 0;   // position of e1 in dec1's reduction (weight) order
 };
 

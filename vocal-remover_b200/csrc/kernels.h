@@ -19,8 +19,10 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 cudaError_t launch_nchw_to_act(const float* x, int C, ActView dst, cudaStream_t stream);
 cudaError_t launch_act_to_nchw(ActView src, int C, float* y, cudaStream_t stream);
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream);
-// channel 0 of `in` -> channel 0 of the 16-channel group `out` (channels 1..15 written as zeros)
-cudaError_t launch_upsample2x_c1(ActView in, ActView out, cudaStream_t stream);
+// fp32 plane in[(n) in_sn][(row) in_sh][col] (inH x inW per image) -> channel 0 of the 16-channel group `out`
+// (channels 1..15 written as zeros), same interpolation arithmetic as launch_upsample2x
+cudaError_t launch_upsample2x_c1(const float* in, int inH, int inW, int64_t in_sn, int64_t in_sh, ActView out,
+                                 cudaStream_t stream);
 cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream);
 cudaError_t launch_broadcast_rows(ActView in, ActView out, cudaStream_t stream);
 
@@ -49,18 +51,22 @@ cudaError_t launch_apply_mask(const float2* spec, const float* mask, int64_t n, 
                               cudaStream_t stream);
 
 // ---- LSTM branch (lstm.cu), reference lib/layers.py:108-133 ------------------------------------
-// 1x1 conv (C -> 1) + BN + ReLU, written time-major fp32: out[n][t][bin]
-cudaError_t launch_lstm_inconv(ActView in, const float* w, float bias, float* out, cudaStream_t stream);
-// C[M][N] = A[M][K] * B[N][K]^T + bias[N]
-cudaError_t launch_gemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
-                           cudaStream_t stream);
+// 1x1 conv (C -> 1), pre-activation sums as an fp32 plane l0[n][bin][t] (the row kernel's epilogue accumulates the same
+// sums when the layer that produces `in` runs there: RowsDot in tc_plan.h)
+cudaError_t launch_lstm_inconv(ActView in, const float* w, float* l0, cudaStream_t stream);
+// xp[(n,t)][gates] = relu(l0[n][:][t] + conv_bias) . wih[gates][:]^T + bih   (gates = 8 * hid)
+cudaError_t launch_lstm_input_projection(const float* l0, float conv_bias, const float* wih, const float* bih, float* xp,
+                                         int N, int T, int bins, int gates, cudaStream_t stream);
 // xp: [n][t][2][4*hid] gate pre-activations (input projection + both biases), whh: [2][4*hid][hid]
 // hs: [n][t][2*hid]
 cudaError_t launch_lstm_recurrence(const float* xp, const float* whh, float* hs, int N, int T, int hid,
                                    cudaStream_t stream);
-// y = relu(scale * (hs . wd^T) + shift) scattered to channel `ch` of dst: dst[n][bin][t][ch]
-cudaError_t launch_lstm_dense(const float* hs, const float* wd, const float* scale, const float* shift, int N, int T,
-                              int K, int bins, ActView dst, int ch, cudaStream_t stream);
+// y[bin][(n,t)] = relu(scale[bin] * (wd[bin][:] . hs[(n,t)][:]) + shift[bin]),  wd: [bins][K], NT = N * T
+cudaError_t launch_lstm_dense(const float* hs, const float* wd, const float* scale, const float* shift, int NT, int K,
+                              int bins, float* y, cudaStream_t stream);
+// y[bin][n][t] -> channel `ch` of dst[n][bin][t][.] (split bf16)
+cudaError_t launch_lstm_plane_to_channel(const float* y, int N, int T, int bins, ActView dst, int ch,
+                                         cudaStream_t stream);
 
 // ---- STFT / iSTFT (fft.cu), reference lib/spec_utils.py:26-31,157-165 (librosa semantics)
 // frames [t0, t1) only (the full-track call is t0 = 0, t1 = T)

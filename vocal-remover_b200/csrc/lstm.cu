@@ -10,7 +10,7 @@
 namespace vr {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void lstm_inconv_kernel(ActView in, const float* __restrict__ w, float bias, float* __restrict__ out) {
+__global__ void lstm_inconv_kernel(ActView in, const float* __restrict__ w, float* __restrict__ out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)in.N * in.H * in.W;
   if (idx >= total) return;
@@ -26,65 +26,191 @@ __global__ void lstm_inconv_kernel(ActView in, const float* __restrict__ w, floa
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc = fmaf(x[i], __ldg(w + c + i), acc);
   }
-  out[((int64_t)n * in.W + t) * in.H + bin] = fmaxf(acc + bias, 0.f);
+  out[idx] = acc;   // [n][bin][t] pre-activation sums; the input projection applies the folded BN bias + ReLU
 }
 
-cudaError_t launch_lstm_inconv(ActView in, const float* w, float bias, float* out, cudaStream_t stream) {
+cudaError_t launch_lstm_inconv(ActView in, const float* w, float* out, cudaStream_t stream) {
   int64_t total = (int64_t)in.N * in.H * in.W;
   if (total == 0) return cudaSuccess;
-  lstm_inconv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, w, bias, out);
+  lstm_inconv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, w, out);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
-// C[M][N] = A[M][K] * B[N][K]^T + bias[N]; 64x64 tile, 16-deep k slab, 256 threads x (4x4).
-__global__ void __launch_bounds__(256) gemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                      const float* __restrict__ bias, float* __restrict__ C, int M,
-                                                      int N, int K) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      int r = i >> 4, c = i & 15;
-      int gm = m0 + r, gn = n0 + r, gk = k0 + c;
-      As[c][r] = (gm < M && gk < K) ? A[(int64_t)gm * K + gk] : 0.f;
-      Bs[c][r] = (gn < N && gk < K) ? B[(int64_t)gn * K + gk] : 0.f;
+// C[M][N] = f(A)[M][K] * B[N][K]^T on a 128x64 tile (256 threads x 8x4 outputs, 16-deep k slab, register prefetch of the
+// next slab, double-buffered shared memory: one barrier per slab), fp32 FMA.  The two GEMMs of the branch:
+//   input projection  xp[(n,t)][gate] = relu(l0[n][:][t] + b0) . wih[gate][:] + bias[gate]
+//                     (ATRANS: A is stored [n][K][T] - the 1x1 convolution's pre-activation sums, t contiguous - and the
+//                      folded BatchNorm bias + ReLU of that convolution are applied while the slab is loaded)
+//   dense + BN + ReLU y[bin][(n,t)]   = relu(scale[bin] * (wd[bin][:] . hs[(n,t)][:]) + shift[bin])
+//                     (computed transposed, so that the (n,t) index, contiguous in the consumer, runs along the store lanes)
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K;
+  int T;              // ATRANS: row m = (n, t) = (m / T, m % T) of A lives at A[(n * K + k) * T + t]
+  float a_bias;       // ATRANS: f(a) = max(a + a_bias, 0)
+  const float* col_bias;
+  const float* row_scale;
+  const float* row_shift;
+  int relu;
+};
+
+template <bool ATRANS>
+__global__ void __launch_bounds__(256) gemm_nt_128x64_kernel(const GemmArgs g) {
+  __shared__ __align__(16) float As[2][16][128 + 4];
+  __shared__ __align__(16) float Bs[2][16][64 + 4];
+  const float* __restrict__ A = g.A;
+  const float* __restrict__ B = g.B;
+  const int M = g.M, N = g.N, K = g.K;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
+  // slab loads.  B (and A when it is row-major): row lr (+64), four k from lk.  ATRANS: k row ak (+8), four m from am.
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int ak = tid >> 5, am = (tid & 31) * 4;
+  const bool vec_k = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(B) | (ATRANS ? 0 : reinterpret_cast<uintptr_t>(A))) & 15) == 0;
+  const bool vec_m = ATRANS && (g.T & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  auto a_at = [&](int m, int k) -> float {   // guarded scalar access, any layout
+    if (m >= M || k >= K) return 0.f;
+    if (!ATRANS) return A[(int64_t)m * K + k];
+    const int n = m / g.T, t = m - n * g.T;
+    return fmaxf(A[((int64_t)n * K + k) * g.T + t] + g.a_bias, 0.f);
+  };
+  auto a_quad_k = [&](int m, int k) -> float4 {   // row-major A: four consecutive k
+    if (vec_k) return m < M && k < K ? *reinterpret_cast<const float4*>(A + (int64_t)m * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return make_float4(a_at(m, k), a_at(m, k + 1), a_at(m, k + 2), a_at(m, k + 3));
+  };
+  auto a_quad_m = [&](int m, int k) -> float4 {   // ATRANS: four consecutive m (same image when T % 4 == 0)
+    if (vec_m) {
+      if (m >= M || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);   // M = n * T is a multiple of 4 as well
+      const int n = m / g.T, t = m - n * g.T;
+      const float4 x = *reinterpret_cast<const float4*>(A + ((int64_t)n * K + k) * g.T + t);
+      return make_float4(fmaxf(x.x + g.a_bias, 0.f), fmaxf(x.y + g.a_bias, 0.f), fmaxf(x.z + g.a_bias, 0.f),
+                         fmaxf(x.w + g.a_bias, 0.f));
     }
-    __syncthreads();
+    return make_float4(a_at(m, k), a_at(m + 1, k), a_at(m + 2, k), a_at(m + 3, k));
+  };
+  auto b_quad = [&](int n, int k) -> float4 {
+    if (vec_k) return n < N && k < K ? *reinterpret_cast<const float4*>(B + (int64_t)n * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = n < N && k + i < K ? B[(int64_t)n * K + k + i] : 0.f;
+    return make_float4(v[0], v[1], v[2], v[3]);
+  };
+  float4 ra0, ra1, rb;
+  auto gload = [&](int k0) {
+    if (ATRANS) {
+      ra0 = a_quad_m(m0 + am, k0 + ak);
+      ra1 = a_quad_m(m0 + am, k0 + ak + 8);
+    } else {
+      ra0 = a_quad_k(m0 + lr, k0 + lk);
+      ra1 = a_quad_k(m0 + lr + 64, k0 + lk);
+    }
+    rb = b_quad(n0 + lr, k0 + lk);
+  };
+  auto sstore = [&](int buf) {
+    if (ATRANS) {
+      *reinterpret_cast<float4*>(&As[buf][ak][am]) = ra0;
+      *reinterpret_cast<float4*>(&As[buf][ak + 8][am]) = ra1;
+    } else {
+      As[buf][lk + 0][lr] = ra0.x; As[buf][lk + 1][lr] = ra0.y; As[buf][lk + 2][lr] = ra0.z; As[buf][lk + 3][lr] = ra0.w;
+      As[buf][lk + 0][lr + 64] = ra1.x; As[buf][lk + 1][lr + 64] = ra1.y;
+      As[buf][lk + 2][lr + 64] = ra1.z; As[buf][lk + 3][lr + 64] = ra1.w;
+    }
+    Bs[buf][lk + 0][lr] = rb.x; Bs[buf][lk + 1][lr] = rb.y; Bs[buf][lk + 2][lr] = rb.z; Bs[buf][lk + 3][lr] = rb.w;
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = (K + 15) >> 4;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) << 4);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
+    if (kt + 1 < nk) sstore(buf ^ 1);
     __syncthreads();
   }
+  const int gn = n0 + tx * 4;
+  float cb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (g.col_bias) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
+    for (int j = 0; j < 4; ++j)
+      if (gn + j < N) cb[j] = g.col_bias[gn + j];
+  }
+  const bool vec_c = (N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty * 8 + i;
     if (gm >= M) continue;
+    const float sc = g.row_scale ? g.row_scale[gm] : 1.f, sf = g.row_scale ? g.row_shift[gm] : 0.f;
+    float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
-      if (gn < N) C[(int64_t)gm * N + gn] = acc[i][j] + (bias ? bias[gn] : 0.f);
+      v[j] = fmaf(acc[i][j] + cb[j], sc, sf);
+      if (g.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    float* dst = g.C + (int64_t)gm * N + gn;
+    if (vec_c && gn + 3 < N) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gn + j < N) dst[j] = v[j];
     }
   }
 }
 
-cudaError_t launch_gemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
-                           cudaStream_t stream) {
-  if (M == 0 || N == 0) return cudaSuccess;
-  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
-  gemm_nt_kernel<<<grid, 256, 0, stream>>>(A, B, bias, C, M, N, K);
+cudaError_t launch_lstm_input_projection(const float* l0, float conv_bias, const float* wih, const float* bih, float* xp,
+                                         int N, int T, int bins, int gates, cudaStream_t stream) {
+  if (N == 0 || T == 0 || gates == 0) return cudaSuccess;
+  GemmArgs g{l0, wih, xp, N * T, gates, bins, T, conv_bias, bih, nullptr, nullptr, 0};
+  dim3 grid((unsigned)ceil_div(gates, 64), (unsigned)ceil_div(N * T, 128));
+  gemm_nt_128x64_kernel<true><<<grid, 256, 0, stream>>>(g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lstm_dense(const float* hs, const float* wd, const float* scale, const float* shift, int NT, int K,
+                              int bins, float* y, cudaStream_t stream) {
+  if (NT == 0 || bins == 0) return cudaSuccess;
+  GemmArgs g{wd, hs, y, bins, NT, K, 0, 0.f, nullptr, scale, shift, 1};
+  dim3 grid((unsigned)ceil_div(NT, 64), (unsigned)ceil_div(bins, 128));
+  gemm_nt_128x64_kernel<false><<<grid, 256, 0, stream>>>(g);
+  return cudaGetLastError();
+}
+
+// the branch output y[bin][n][t] -> channel `ch` of dst (staged dec1 layout: the LSTM channel of d2)
+__global__ void lstm_plane_to_channel_kernel(const float* __restrict__ y, int N, int T, int bins, ActView dst, int ch) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)bins * N * T) return;
+  const int t = (int)(idx % T);
+  const int64_t r = idx / T;
+  const int n = (int)(r % N), bin = (int)(r / N);
+  const int64_t o = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)t * dst.sw + ch;
+  split_bf16(y[idx], dst.hi[o], dst.lo[o]);
+}
+
+cudaError_t launch_lstm_plane_to_channel(const float* y, int N, int T, int bins, ActView dst, int ch,
+                                         cudaStream_t stream) {
+  const int64_t total = (int64_t)bins * N * T;
+  if (total == 0) return cudaSuccess;
+  lstm_plane_to_channel_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(y, N, T, bins, dst, ch);
   return cudaGetLastError();
 }
 
@@ -149,32 +275,6 @@ cudaError_t launch_lstm_recurrence(const float* xp, const float* whh, float* hs,
     case 128: lstm_recurrence_kernel<128><<<grid, 512, 0, stream>>>(xp, whh, hs, T); break;
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// grid (T, N); block = 128 threads striding over bins.  wd is stored transposed: wdT[k][bin].
-__global__ void lstm_dense_kernel(const float* __restrict__ hs, const float* __restrict__ wdT,
-                                  const float* __restrict__ scale, const float* __restrict__ shift, int T, int K,
-                                  int bins, ActView dst, int ch) {
-  extern __shared__ float h_s[];
-  const int t = blockIdx.x, n = blockIdx.y;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) h_s[k] = hs[((int64_t)n * T + t) * K + k];
-  __syncthreads();
-  for (int bin = threadIdx.x; bin < bins; bin += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc = fmaf(h_s[k], __ldg(wdT + (int64_t)k * bins + bin), acc);
-    float y = fmaxf(fmaf(acc, scale[bin], shift[bin]), 0.f);
-    int64_t o = (int64_t)n * dst.sn + (int64_t)bin * dst.sh + (int64_t)t * dst.sw + ch;
-    split_bf16(y, dst.hi[o], dst.lo[o]);
-  }
-}
-
-cudaError_t launch_lstm_dense(const float* hs, const float* wdT, const float* scale, const float* shift, int N, int T,
-                              int K, int bins, ActView dst, int ch, cudaStream_t stream) {
-  if (N == 0) return cudaSuccess;
-  dim3 grid((unsigned)T, (unsigned)N);
-  lstm_dense_kernel<<<grid, 128, K * sizeof(float), stream>>>(hs, wdT, scale, shift, T, K, bins, dst, ch);
   return cudaGetLastError();
 }
 
