@@ -460,43 +460,30 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         f_base = (int64_t)(mt / p.tiles_h) * p.xsn + (int64_t)f_X * p.xsw + j * 8;
       };
       fetch_tile();
-      // Rows are produced in PAIRS (R + 2 is even, so a pair never straddles a chunk or a tile): fence.proxy.async compiles to
-      // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR waits for every global load of the thread that is still in
-      // flight, so with one fence per row the row time could not drop below the load latency.  With one fence per pair the
-      // loads of rows 2k+4, 2k+5 are issued right after the fence of pair k and have the whole of pair k+1 to land.
-      // qv[i] = row i of the pair being written next, already blended vertically (the blend runs when the pair moves up:
-      // right after the fence, which has waited for its loads anyway); n*[i] = source rows of row i of the pair after it.
-      bf16x8 nah[2], nch[2], nal[2], ncl[2];   // rows y0 / y1 of the hi plane, rows y0 / y1 of the lo plane
-      float qv[2][8];
-      float n_ly[2] = {0.f, 0.f};
-      bool n_ok[2] = {false, false};
-#pragma unroll
-      for (int i = 0; i < 2; ++i) nah[i] = nch[i] = nal[i] = ncl[i] = make_uint4(0, 0, 0, 0);
-      auto fetch = [&](const int i) {
-        if (n_ok[i]) {
-          float a[8], c[8];
-          unpack8(nah[i], nal[i], a);
-          unpack8(nch[i], ncl[i], c);
-          const float ly = n_ly[i], hy = 1.f - n_ly[i];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) qv[i][e] = hy * a[e] + ly * c[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) qv[i][e] = 0.f;
-        }
+      // Two rows are in flight: the loads of row k+2 are issued right after the proxy fence of row k (fence.proxy.async
+      // compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR waits for every global load still in flight), so that
+      // they have the whole of row k+1 to land before the next fence.  q* = row k+1, n* = row k+2.
+      bf16x8 qah, qch, qal, qcl, nah, nch, nal, ncl;   // rows y0 / y1 of the hi plane, rows y0 / y1 of the lo plane
+      float q_ly = 0.f, n_ly = 0.f;
+      bool q_ok = false, n_ok = false;
+      qah = qch = qal = qcl = nah = nch = nal = ncl = make_uint4(0, 0, 0, 0);
+      auto fetch = [&]() {
+        qah = nah; qch = nch; qal = nal; qcl = ncl;
+        q_ly = n_ly;
+        q_ok = n_ok;
         const int h = f_h0 + f_r;
         const bool grp = (chunk_groups(p.kmask, f_cc) >> j) & 1u;   // channel group without weights: zeros are written
-        n_ok[i] = f_tile < p.total_tiles && h >= 0 && h < p.H && grp && f_px;
-        if (n_ok[i]) {
+        n_ok = f_tile < p.total_tiles && h >= 0 && h < p.H && grp && f_px;
+        if (n_ok) {
           const float fy = p.up_sh * h;
           const int y0 = (int)fy;
-          n_ly[i] = fy - (float)y0;
+          n_ly = fy - (float)y0;
           const int64_t o0 = f_base + (int64_t)y0 * p.xsh + f_cc * 32;
           const int64_t o1 = o0 + (y0 < p.xH - 1 ? p.xsh : 0);
-          nah[i] = ld128(p.x_hi + o0);
-          nch[i] = ld128(p.x_hi + o1);
-          nal[i] = ld128(p.x_lo + o0);
-          ncl[i] = ld128(p.x_lo + o1);
+          nah = ld128(p.x_hi + o0);
+          nch = ld128(p.x_hi + o1);
+          nal = ld128(p.x_lo + o0);
+          ncl = ld128(p.x_lo + o1);
         }
         if (++f_r == R + 2) {
           f_r = 0;
@@ -507,10 +494,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
           }
         }
       };
-      static_assert((R + 2) % 2 == 0, "rows are produced in pairs");
       if (fills > 0) {
-        fetch(0); fetch(1);   // pair 0
-        fetch(0); fetch(1);   // pair 1 (pair 0 moves to q*)
+        fetch();   // row 0
+        fetch();   // row 1 (row 0 moves to q*)
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int mt = tile / p.n_tiles;
@@ -549,59 +535,60 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         }
         const bool last_px = X >= p.xW - 1;   // x1 = x0 on the last source pixel (upsample2x_kernel)
         for (int cc = 0; cc < p.up_chunks; ++cc) {
-          for (int r = 0; r < R + 2; r += 2) {
+          for (int r = 0; r < R + 2; ++r) {
             const unsigned long long t0 = tr ? clock64() : 0ull;
-            unsigned long long t_wait = 0ull;
-            uint32_t full_bar[2];
+            float v[8];
+            if (q_ok) {
+              float a[8], c[8];
+              unpack8(qah, qal, a);
+              unpack8(qch, qcl, c);
+              const float ly = q_ly, hy = 1.f - q_ly;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float* v = qv[i];
-              float nv[8];
+              for (int i = 0; i < 8; ++i) v[i] = hy * a[i] + ly * c[i];
+            } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float t = __shfl_down_sync(0xffffffffu, v[e], 4);
-                nv[e] = last_px ? v[e] : t;
-              }
-              const unsigned long long t1 = tr ? clock64() : 0ull;
-              mbar_wait(aempty0 + (uint32_t)as * 8u, aph ^ 1u);
-              if (tr) t_wait += clock64() - t1;
-              uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * kASlot;
+              for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            }
+            float nv[8];
 #pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                if (e_off[k] < 0) continue;
-                const float lx = e_lx[k], hx = 1.f - lx;
-                float y[8];
+            for (int i = 0; i < 8; ++i) {
+              const float t = __shfl_down_sync(0xffffffffu, v[i], 4);
+              nv[i] = last_px ? v[i] : t;
+            }
+            const unsigned long long t1 = tr ? clock64() : 0ull;
+            mbar_wait(aempty0 + (uint32_t)as * 8u, aph ^ 1u);
+            const unsigned long long t2 = tr ? clock64() : 0ull;
+            uint8_t* slot = smem_raw + (a_base - smem_u32(smem_raw)) + (size_t)as * kASlot;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = hx * v[e] + lx * nv[e];
-                bf16x8 oh, ol;
-                split8(y, oh, ol);
-                *reinterpret_cast<uint4*>(slot + e_off[k]) = oh;
-                *reinterpret_cast<uint4*>(slot + kAPlane + e_off[k]) = ol;
-              }
-              if (z_off >= 0) {
-                *reinterpret_cast<uint4*>(slot + z_off) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(slot + kAPlane + z_off) = make_uint4(0, 0, 0, 0);
-              }
-              full_bar[i] = afull0 + (uint32_t)as * 8u;
-              if (++as == p.n_uslots) {
-                as = 0;
-                aph ^= 1u;
-              }
+            for (int k = 0; k < 3; ++k) {
+              if (e_off[k] < 0) continue;
+              const float lx = e_lx[k], hx = 1.f - lx;
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = hx * v[i] + lx * nv[i];
+              bf16x8 oh, ol;
+              split8(y, oh, ol);
+              *reinterpret_cast<uint4*>(slot + e_off[k]) = oh;
+              *reinterpret_cast<uint4*>(slot + kAPlane + e_off[k]) = ol;
+            }
+            if (z_off >= 0) {
+              *reinterpret_cast<uint4*>(slot + z_off) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(slot + kAPlane + z_off) = make_uint4(0, 0, 0, 0);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(full_bar[0]);
-              mbar_arrive(full_bar[1]);
-            }
-            fetch(0);   // the pair after the next one (after the fence, see above); past the last row it only shifts
-            fetch(1);
+            if (lane == 0) mbar_arrive(afull0 + (uint32_t)as * 8u);
+            fetch();   // row k+2 (after the fence, see above); past the last row it only shifts the pipeline
             if (tr && lane == 0 && tn < kTraceEvents) {
               g_rows_trace[(2 * kTraceEvents + tn) * 3 + 0] = t0;
-              g_rows_trace[(2 * kTraceEvents + tn) * 3 + 1] = t_wait;   // cycles spent waiting for the two slots
+              g_rows_trace[(2 * kTraceEvents + tn) * 3 + 1] = t2 - t1;   // cycles spent waiting for the slot
               g_rows_trace[(2 * kTraceEvents + tn) * 3 + 2] = clock64();
             }
             ++tn;
+            if (++as == p.n_uslots) {
+              as = 0;
+              aph ^= 1u;
+            }
           }
         }
       }

@@ -151,7 +151,10 @@ cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream) {
 }
 
 // Single-channel variant for the LSTM branch (lib/nets.py:38, layers.py:52): the source is the fp32 plane in[bin][n][t] the dense GEMM wrote
-// (strides in_sn, in_sh in floats, t contiguous); the result goes to channel 0 of a 16-channel group (15 zeros).
+// (strides in_sn, in_sh in floats, t contiguous); the result goes to channel 0 of a G-channel group (G - 1 zeros), G = 16
+// inside a concat buffer (32-byte sectors) or 8 for the buffer of its own that the row kernel reads through a second
+// tensor map (TMA zero-fills the rest of the chunk).
+template <int G>
 __global__ void __launch_bounds__(256) upsample2x_c1_kernel(const float* __restrict__ in, int inH, int inW, int64_t in_sn,
                                                             int64_t in_sh, ActView out, float sh, float sw) {
   const int wo = blockIdx.y * blockDim.x + threadIdx.x;   // rows on grid.x: N * H exceeds the 65535 limit of grid.y
@@ -171,19 +174,28 @@ __global__ void __launch_bounds__(256) upsample2x_c1_kernel(const float* __restr
   split_bf16(y, h, l);
   const int64_t oo = (int64_t)n * out.sn + (int64_t)ho * out.sh + (int64_t)wo * out.sw;
   const uint4 z = make_uint4(0, 0, 0, 0);
-  st256(out.hi + oo, make_uint4((uint32_t)__bfloat16_as_ushort(h), 0, 0, 0), z);
-  st256(out.lo + oo, make_uint4((uint32_t)__bfloat16_as_ushort(l), 0, 0, 0), z);
+  if (G == 16) {
+    st256(out.hi + oo, make_uint4((uint32_t)__bfloat16_as_ushort(h), 0, 0, 0), z);
+    st256(out.lo + oo, make_uint4((uint32_t)__bfloat16_as_ushort(l), 0, 0, 0), z);
+  } else {
+    st128(out.hi + oo, make_uint4((uint32_t)__bfloat16_as_ushort(h), 0, 0, 0));
+    st128(out.lo + oo, make_uint4((uint32_t)__bfloat16_as_ushort(l), 0, 0, 0));
+  }
 }
 
 cudaError_t launch_upsample2x_c1(const float* in, int inH, int inW, int64_t in_sn, int64_t in_sh, ActView out,
                                  cudaStream_t stream) {
   if ((int64_t)out.N * out.H * out.W == 0) return cudaSuccess;
-  if (out.C != 16 || out.sw % 16 || ((reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo)) & 31))
+  const uintptr_t align = reinterpret_cast<uintptr_t>(out.hi) | reinterpret_cast<uintptr_t>(out.lo);
+  if (!((out.C == 16 && out.sw % 16 == 0 && (align & 31) == 0) || (out.C == 8 && out.sw % 8 == 0 && (align & 15) == 0)))
     return cudaErrorInvalidValue;
   const float sh = out.H > 1 ? (float)(inH - 1) / (float)(out.H - 1) : 0.f;
   const float sw = out.W > 1 ? (float)(inW - 1) / (float)(out.W - 1) : 0.f;
   dim3 grid((unsigned)(out.N * out.H), (unsigned)ceil_div(out.W, 256));
-  upsample2x_c1_kernel<<<grid, 256, 0, stream>>>(in, inH, inW, in_sn, in_sh, out, sh, sw);
+  if (out.C == 16)
+    upsample2x_c1_kernel<16><<<grid, 256, 0, stream>>>(in, inH, inW, in_sn, in_sh, out, sh, sw);
+  else
+    upsample2x_c1_kernel<8><<<grid, 256, 0, stream>>>(in, inH, inW, in_sn, in_sh, out, sh, sw);
   return cudaGetLastError();
 }
 

@@ -212,7 +212,7 @@ bool Engine::build_basenet(BaseNetPlan& P, const std::string& prefix, int nin, c
   P.e1_coff = P.skip_only ? 0 : P.e1_off;           // position of e1 in the cat1 buffer
   P.lstm_coff = !P.skip_only ? 2 * n : P.lstm_own ? 0 : n;
   P.cat1 = make_buffer(Nb, H, W, !P.skip_only ? c1 : P.lstm_own ? n : round_up(n + lg, 32));
-  if (P.lstm_own) P.lstm_up = make_buffer(Nb, H, W, lg);
+  if (P.lstm_own) P.lstm_up = make_buffer(Nb, H, W, 8);   // 8-channel group: the row kernel's TMA box zero-fills the rest
   P.t2 = make_buffer(Nb, H / 2, W / 2, 2 * n);
   P.cat2 = make_buffer(Nb, H / 2, W / 2, 6 * n);
   P.t3 = make_buffer(Nb, H / 4, W / 4, 4 * n);

@@ -19,8 +19,8 @@ cudaError_t launch_pack_mag_from_float(const float* mag, int bins, int max_bin, 
 cudaError_t launch_nchw_to_act(const float* x, int C, ActView dst, cudaStream_t stream);
 cudaError_t launch_act_to_nchw(ActView src, int C, float* y, cudaStream_t stream);
 cudaError_t launch_upsample2x(ActView in, ActView out, cudaStream_t stream);
-// fp32 plane in[(n) in_sn][(row) in_sh][col] (inH x inW per image) -> channel 0 of the 16-channel group `out`
-// (channels 1..15 written as zeros), same interpolation arithmetic as launch_upsample2x
+// fp32 plane in[(n) in_sn][(row) in_sh][col] (inH x inW per image) -> channel 0 of the 16- or 8-channel group `out`
+// (the other channels written as zeros), same interpolation arithmetic as launch_upsample2x
 cudaError_t launch_upsample2x_c1(const float* in, int inH, int inW, int64_t in_sn, int64_t in_sh, ActView out,
                                  cudaStream_t stream);
 cudaError_t launch_pool_freq_mean(ActView in, ActView out, cudaStream_t stream);

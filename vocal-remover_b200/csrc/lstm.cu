@@ -246,13 +246,13 @@ __global__ void __launch_bounds__(4 * HID) lstm_recurrence_kernel(const float* _
       g2 = fmaf(wrow[k + 2], h_s[k + 2], g2);
       g3 = fmaf(wrow[k + 3], h_s[k + 3], g3);
     }
-    g_s[j] = (g0 + g1) + (g2 + g3);
+    // every thread applies its own gate's non-linearity (i, f, o: sigmoid; g: tanh) - one transcendental per thread in
+    // parallel instead of five in sequence on the HID combining threads
+    const float pre = (g0 + g1) + (g2 + g3);
+    g_s[j] = (j >= 2 * HID && j < 3 * HID) ? tanhf(pre) : sigmoid_acc(pre);
     __syncthreads();
     if (j < HID) {
-      float ig = sigmoid_acc(g_s[j]);
-      float fg = sigmoid_acc(g_s[HID + j]);
-      float gg = tanhf(g_s[2 * HID + j]);
-      float og = sigmoid_acc(g_s[3 * HID + j]);
+      const float ig = g_s[j], fg = g_s[HID + j], gg = g_s[2 * HID + j], og = g_s[3 * HID + j];
       c = fg * c + ig * gg;
       float h = og * tanhf(c);
       h_s[j] = h;
