@@ -43,10 +43,10 @@ SR = 44100
 SECONDS_PER_GPU = 240.0
 CONV_FLOP_PER_WINDOW = 135.714e9
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the tensor-core convolution launches of the round-2 ncu launch
-# list (profiles/r02_launches_bench.csv: 128.9 GB over the 141 windows that bench run pushes through the net; round 1
+# list (profiles/r02_launches_bench.csv: 127.3 GB over the 141 windows that bench run pushes through the net; round 1
 # measured 0.879 GB with the LSTM channel still interleaved into the skip tensor, 1.225 GB before the decoder upsample
 # was fused); the un-fused minimum of SURVEY 8(d) is 1.142 GB/window.
-CONV_DRAM_BYTES_PER_WINDOW = 0.914e9
+CONV_DRAM_BYTES_PER_WINDOW = 0.903e9
 GOLDEN = os.path.join(ROOT, 'tests', 'golden', 'ref_10s_default.npz')
 
 
@@ -356,6 +356,18 @@ def run_gpu(args):
     value = seconds / (ms_step * 1e-3)
     ms_median = sorted(per_step)[len(per_step) // 2]
 
+    # ---- roofline pass, right after the timed steps (same clocks / thermal state): one more step of the same
+    # workload with a CUDA event pair around every convolution launch (recorded inside the library on the launching
+    # stream); the two band streams are serialised while profiling so each pair brackets exactly one kernel.
+    import ctypes
+    prof = (ctypes.c_double * 6)()
+    ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 1), 'vr_profile_enable')
+    prof_ms = timed(step_device, 1)
+    ctx.check(ctx.lib.vr_profile_read(ctx.handle, prof), 'vr_profile_read')
+    if args.layers and rank == 0:
+        write_layer_table(ctx, args.layers)
+    ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 0), 'vr_profile_enable')
+
     # ---- BASELINE configs[3]: the same track with --tta (second, half-window-shifted pass; inference.py:83-102) ----
     def step_tta():
         return vr_dist.separate_wave(sp, d_wave, tta=True, world=world, rank=rank)
@@ -387,18 +399,6 @@ def run_gpu(args):
         del d_long
         torch.cuda.empty_cache()
 
-    # ---- roofline pass: one more step of the same workload with a CUDA event pair around every convolution
-    # launch (recorded inside the library on the launching stream); the two band streams are serialised while
-    # profiling so each pair brackets exactly one kernel.
-    import ctypes
-    prof = (ctypes.c_double * 6)()
-    ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 1), 'vr_profile_enable')
-    prof_ms = timed(step_device, 1)
-    ctx.check(ctx.lib.vr_profile_read(ctx.handle, prof), 'vr_profile_read')
-    if args.layers and rank == 0:
-        write_layer_table(ctx, args.layers)
-    ctx.check(ctx.lib.vr_profile_enable(ctx.handle, 0), 'vr_profile_enable')
-
     # ---- end to end through the public host-buffer API (pinned host wave -> pinned host stems) ----
     Lo = 1024 * (T - 1)
     h_inst = torch.empty((2, Lo), dtype=torch.float32).pin_memory()
@@ -429,7 +429,7 @@ def run_gpu(args):
                           'bf16x3 split precision)',
                 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                 'traffic': CONV_DRAM_BYTES_PER_WINDOW * n_windows / world / max(1.0, tc_n),
-                'traffic_note': 'average DRAM bytes per convolution launch = 0.914 GB per window (ncu, '
+                'traffic_note': 'average DRAM bytes per convolution launch = 0.903 GB per window (ncu, '
                                 'profiles/r02_launches_bench.csv) x windows per rank / launches',
                 'peak_source': peak_src,
                 'note': 'achieved = algorithmic conv FLOPs (real channel counts, 1x per product; the kernel issues 3 '

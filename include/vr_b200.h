@@ -124,6 +124,18 @@ VR_API int vr_separate_wave(vr_ctx* ctx, const float* wave, int64_t L, int32_t t
 VR_API int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_t tta, float* inst_host,
                           float* voc_host, void* stream);
 
+/* The sample-rate conversion inside librosa.load(path, sr=args.sr, res_type='kaiser_fast') (inference.py:136-138,
+ * pseudo.py:47-50) = resampy.resample(y, orig_sr, sr, filter='kaiser_fast'): x [channels][n_in] -> y [channels][n_out],
+ * n_out = (int64)(n_in * sample_ratio), sample_ratio = sr / orig_sr.  win / delta: DEVICE float64 arrays of nwin entries -
+ * the half filter table (already multiplied by sample_ratio when it is < 1) and its first difference - with
+ * table_per_crossing entries per zero crossing, as resampy.core.resample prepares them (lib/audio_io.py builds the
+ * documented kaiser_fast table; a table taken from an installed resampy can be passed instead).  ctx may be NULL
+ * (audio is loaded before a model exists): the call then runs on the calling thread's current device and its error
+ * message is read with vr_last_error(NULL).  SURVEY 8(f) rank 2.                                            */
+VR_API int vr_resample(vr_ctx* ctx, const float* x, int32_t channels, int64_t n_in, float* y, int64_t n_out,
+                       double sample_ratio, const double* win, const double* delta, int32_t nwin,
+                       int32_t table_per_crossing, void* stream);
+
 /* Multi-GPU mask exchange over NVLink peer memory (one process per GPU).  The owner (rank 0) allocates the
  * whole-track mask with vr_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it
  * with vr_shared_open and passes the mapped pointer as `mask` to vr_separate_windows, so the mask epilogue

@@ -7,6 +7,7 @@
 
 #include "../../include/vr_b200.h"
 #include "engine.h"
+#include "kernels.h"
 #include "tc_plan.h"
 
 struct vr_ctx {
@@ -188,6 +189,25 @@ int vr_separate_wave_host(vr_ctx* ctx, const float* wave_host, int64_t L, int32_
                           float* voc_host, void* stream) {
   CHECK_CTX(ctx);
   return done(ctx, ctx->eng->separate_wave_host(wave_host, L, tta, inst_host, voc_host, (cudaStream_t)stream));
+}
+
+int vr_resample(vr_ctx* ctx, const float* x, int32_t channels, int64_t n_in, float* y, int64_t n_out, double sample_ratio,
+                const double* win, const double* delta, int32_t nwin, int32_t table_per_crossing, void* stream) {
+  // ctx may be NULL (audio is usually loaded before a model context exists): the call then runs on the calling
+  // thread's current device and its error message is read with vr_last_error(NULL)
+  auto bad = [&](const std::string& m) {
+    if (ctx) return fail(ctx, m);
+    g_create_err = m;
+    return -1;
+  };
+  if (!x || !y || !win || !delta) return bad("vr_resample: null pointer");
+  if (n_out != (int64_t)((double)n_in * sample_ratio))
+    return bad("vr_resample: n_out must be int(n_in * sample_ratio) (resampy.core.resample)");
+  if (ctx && ctx->eng) cudaSetDevice(ctx->eng->cfg().device);
+  cudaError_t e = vr::launch_resample_sinc(x, channels, n_in, y, n_out, sample_ratio, win, delta, nwin, table_per_crossing,
+                                           (cudaStream_t)stream);
+  if (e != cudaSuccess) return bad(std::string("vr_resample: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 int vr_shared_alloc(vr_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* handle64) {

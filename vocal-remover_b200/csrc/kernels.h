@@ -83,4 +83,10 @@ cudaError_t launch_istft_ola(const float* frames_a, const float* frames_b, int n
                              int64_t t_first, int64_t nfr, int64_t s0, int64_t s1, float* wave_a, float* wave_b,
                              const float* window, cudaStream_t stream);
 
+// ---- sample-rate conversion (resample.cu), resampy.resample(filter='kaiser_fast') behind librosa.load ----------
+// x [C][n_in] -> y [C][n_out], n_out = int(n_in * sample_ratio); win / delta: the (ratio-scaled) half filter table and
+// its first difference, nwin entries, num_table entries per zero crossing (oracle/resample_oracle.py: prepare)
+cudaError_t launch_resample_sinc(const float* x, int C, int64_t n_in, float* y, int64_t n_out, double sample_ratio,
+                                 const double* win, const double* delta, int nwin, int num_table, cudaStream_t stream);
+
 }  // namespace vr

@@ -188,7 +188,7 @@ def main():
     print('done')
 
     print('loading wave source...', end=' ')
-    X, sr = audio_io.load(args.input, sr=args.sr, mono=False, dtype=np.float32)
+    X, sr = audio_io.load(args.input, sr=args.sr, mono=False, dtype=np.float32, device=device)
     basename = os.path.splitext(os.path.basename(args.input))[0]
     print('done')
 

@@ -28,6 +28,7 @@ SIGNATURES = {
     'vr_finalize_weights': (c_i32, [c_vp]),
     'vr_stft': (c_i32, [c_vp, c_fp, c_i64, c_vp, c_i64, c_fp, c_vp]),
     'vr_istft': (c_i32, [c_vp, c_vp, c_i64, c_fp, c_vp]),
+    'vr_resample': (c_i32, [c_vp, c_fp, c_i32, c_i64, c_fp, c_i64, ctypes.c_double, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'vr_predict_mask': (c_i32, [c_vp, c_fp, c_i32, c_fp, c_vp]),
     'vr_forward': (c_i32, [c_vp, c_fp, c_i32, c_fp, c_vp]),
     'vr_normaliser': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_fp, c_vp]),

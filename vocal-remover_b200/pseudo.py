@@ -99,8 +99,8 @@ def main():
         print(basename)
 
         print('loading wave source...', end=' ')
-        X, sr = audio_io.load(mix_path, sr=args.sr, mono=False, dtype=np.float32)
-        y, sr = audio_io.load(inst_path, sr=args.sr, mono=False, dtype=np.float32)
+        X, sr = audio_io.load(mix_path, sr=args.sr, mono=False, dtype=np.float32, device=device)
+        y, sr = audio_io.load(inst_path, sr=args.sr, mono=False, dtype=np.float32, device=device)
         print('done')
 
         if X.ndim == 1:
