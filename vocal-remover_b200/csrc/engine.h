@@ -81,8 +81,8 @@ struct BaseNetPlan {
   // skip_only: dec1's upsample of h is fused into the row kernel and d2 = [h 2n] only; the single LSTM channel is
   // up-sampled by a small kernel from lstm.y (half resolution, fp32 plane) into a 16-channel group at full
   // resolution: channels [n, n+16) of cat1 = [e1 n | up(lstm) 1 + 15 zeros] when e1 leaves room in its chunk (n = 16),
-  // else the buffer lstm_up of its own (n = 32: cat1 = [e1 n] stays dense for enc2.conv1, and the row kernel reads the
-  // group as its last chunk through a second tensor map).  Otherwise (CUDA-core validation mode, nets whose
+  // else an 8-channel group in the buffer lstm_up of its own (n = 32, 64: cat1 = [e1 n] stays dense for enc2.conv1, and
+  // the row kernel reads the group as its last chunk through a second tensor map whose box TMA zero-fills).  Otherwise (CUDA-core validation mode, nets whose
   // 2n is not a multiple of 32): cat1 = [up(h) 2n | up(lstm) 1 + 15 zeros | e1 n | pad], d2 = [h 2n | lstm 1 | zeros].
   bool skip_only = false;
   int e1_coff = 0;          // channel offset of e1 inside cat1

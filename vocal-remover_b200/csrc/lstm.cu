@@ -1,9 +1,11 @@
 // LSTM branch of BaseNet (reference lib/layers.py:108-133, wired at lib/nets.py:23,38):
 //   1x1 conv (2n -> 1) + BN + ReLU  ->  (T, N, bins)  ->  BiLSTM(hidden = nout_lstm/2, gate order i,f,g,o)
 //   -> Linear(nout_lstm -> bins) + BatchNorm1d(eval) + ReLU -> one extra channel of the dec1 input.
-// 0.18 % of the FLOPs but a 128-step sequential dependency: the input projection is hoisted into
-// one GEMM, and the recurrence runs as one persistent CTA per (window, direction) with its W_hh row
-// held in registers and h exchanged through shared memory.  All math fp32 with accurate expf/tanhf.
+// 0.18 % of the FLOPs but a 128-step sequential dependency on the critical path between dec2 and dec1: the 1x1
+// convolution is accumulated by dec2's epilogue (conv_tc_rows.cu; lstm_inconv_kernel only when dec2 runs elsewhere), the
+// input projection is hoisted into one GEMM, the recurrence runs as one persistent CTA per (window, direction) with its
+// W_hh row held in registers and h exchanged through shared memory, and the dense layer is the same GEMM computed
+// transposed into an fp32 plane.  All math fp32 with accurate expf/tanhf.
 #include "common.cuh"
 #include "kernels.h"
 
