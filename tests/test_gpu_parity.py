@@ -63,6 +63,36 @@ def test_istft_matches_oracle_and_roundtrip(wave10):
     assert w0.shape == (w.shape[1],) and np.abs(w0 - wr[0]).max() < 5e-6
 
 
+def test_frame_ranges_match_the_whole_track_calls(wave10):
+    """The shard-sized entry points of the multi-GPU path (vr_stft_range, vr_apply_mask_istft_range) on ONE GPU: frame
+    ranges with odd starts and lengths that are not multiples of the four frames a CTA of the n_fft = 2048 kernels
+    transforms must reproduce the whole-track calls exactly (the same kernels, other alignment / tail branches)."""
+    from lib import _native, spec_utils
+    ctx = spec_utils._spectral_ctx(2048, 1024)
+    dev = _dev()
+    L = wave10.shape[1]
+    T = 1 + L // 1024
+    d_wave = torch.from_numpy(wave10).to(dev)
+    st = _native.stream_ptr()
+    full = torch.empty((2, 1025, T), dtype=torch.complex64, device=dev)
+    ctx.check(ctx.lib.vr_stft(ctx.handle, _native.ptr(d_wave), L, _native.ptr(full), T, None, st), 'vr_stft')
+    part = torch.zeros_like(full)
+    for a, b in ((0, 3), (3, 10), (10, 11), (11, T - 5), (T - 5, T)):
+        ctx.check(ctx.lib.vr_stft_range(ctx.handle, _native.ptr(d_wave), L, _native.ptr(part), T, a, b, st), 'vr_stft_range')
+    assert torch.equal(torch.view_as_real(part), torch.view_as_real(full))
+    mask = torch.rand((2, 1025, T), device=dev)
+    Lo = 1024 * (T - 1)
+    ia, va = torch.empty((2, Lo), device=dev), torch.empty((2, Lo), device=dev)
+    ctx.check(ctx.lib.vr_apply_mask_istft(ctx.handle, _native.ptr(full), _native.ptr(mask), T, _native.ptr(ia),
+                                          _native.ptr(va), st), 'vr_apply_mask_istft')
+    ib, vb = torch.zeros_like(ia), torch.zeros_like(va)
+    for k0, k1 in ((0, 1), (1, 6), (6, 7), (7, T - 4), (T - 4, T - 1)):
+        ctx.check(ctx.lib.vr_apply_mask_istft_range(ctx.handle, _native.ptr(full), _native.ptr(mask), T, k0, k1,
+                                                    _native.ptr(ib), _native.ptr(vb), st), 'vr_apply_mask_istft_range')
+    torch.cuda.synchronize()
+    assert torch.equal(ia, ib) and torch.equal(va, vb)
+
+
 def test_stft_ragged_and_small_fft():
     from lib import spec_utils
     from oracle import stft_oracle
