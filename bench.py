@@ -401,8 +401,21 @@ def run_gpu(args):
 
     # ---- end to end through the public host-buffer API (pinned host wave -> pinned host stems) ----
     Lo = 1024 * (T - 1)
-    h_inst = torch.empty((2, Lo), dtype=torch.float32).pin_memory()
-    h_voc = torch.empty((2, Lo), dtype=torch.float32).pin_memory()
+    # N > 1: one page-locked buffer shared by all ranks (POSIX shared memory registered with CUDA on every rank), so that
+    # each rank's device-to-host copy lands its span in the SAME buffer and the stems come out assembled; falls back to
+    # per-rank pinned buffers (spans not assembled) when the node refuses it.
+    shared_host = None
+    if world > 1:
+        try:
+            shared_host = vr_dist.SharedHostBuffer.create((2, 2, Lo), world, rank)
+        except Exception as exc:   # never let the optional buffer take the bench down
+            print('bench: shared host buffer unavailable (%s); per-rank pinned buffers' % exc, file=sys.stderr)
+            shared_host = None
+    if shared_host is not None:
+        h_inst, h_voc = shared_host.tensor[0], shared_host.tensor[1]
+    else:
+        h_inst = torch.empty((2, Lo), dtype=torch.float32).pin_memory()
+        h_voc = torch.empty((2, Lo), dtype=torch.float32).pin_memory()
 
     def step_e2e():
         vr_dist.separate_wave_host(sp, h_wave, h_inst, h_voc, tta=False, world=world, rank=rank)
@@ -419,6 +432,16 @@ def run_gpu(args):
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
+    # the stems assembled in the shared host buffer against the device-resident single-GPU result of the same track
+    assembled_diff = None
+    if shared_host is not None:
+        if rank == 0:
+            i1, v1 = vr_dist.separate_wave(sp, d_wave, tta=False, world=1, rank=0)
+            assembled_diff = max((h_inst - i1.cpu()).abs().max().item(), (h_voc - v1.cpu()).abs().max().item())
+            del i1, v1
+        barrier()
+        h_inst = h_voc = None
+        shared_host.close(world)
 
     peak_tf, peak_hbm, peak_src = measured_peaks()
     tc_ms, tc_flops, tc_n, cc_ms, cc_flops, cc_n = [float(x) for x in prof]
@@ -472,7 +495,11 @@ def run_gpu(args):
             'e2e': {'value': seconds / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(2 * L * 4),
                     'd2h_bytes_per_step': int(2 * 2 * Lo * 4),
                     'note': 'bytes are totals over all ranks; with N > 1 every rank moves only its own slice of the '
-                            'wave / stems over its own PCIe link (lib/distributed.py, sharded mode)'},
+                            'wave / stems over its own PCIe link (lib/distributed.py, sharded mode)',
+                    'assembled': (None if world == 1 else
+                                  {'shared_host_buffer': assembled_diff is not None, 'max_diff_vs_single_gpu': assembled_diff,
+                                   'what': 'every rank copies its span into ONE page-locked buffer (POSIX shared memory '
+                                           'registered with CUDA); compared on rank 0 with the single-GPU stems'})},
             'gpu_launches': int(launches),
             'parity': parity,
             'mgpu_check': check,

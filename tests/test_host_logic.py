@@ -119,6 +119,34 @@ def test_sharded_gather_world_size_2_gloo(tmp_path):
     assert torch.equal(mask[0, 0], torch.arange(n_frames, dtype=torch.float32))
 
 
+def _shared_host_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from lib import distributed
+    buf = distributed.SharedHostBuffer.create((2, 1000), world, rank, register=False)
+    assert buf is not None and buf.tensor.shape == (2, 1000)
+    lo, hi = (0, 400) if rank == 0 else (400, 1000)     # every rank lands its own span, like separate_wave_host
+    buf.tensor[:, lo:hi] = torch.arange(lo, hi, dtype=torch.float32)
+    dist.barrier()
+    whole = buf.tensor.clone()                          # ... and every rank sees the assembled buffer
+    assert torch.equal(whole[0], torch.arange(1000, dtype=torch.float32)) and torch.equal(whole[1], whole[0])
+    if rank == 1:
+        torch.save(whole, tmp)
+    buf.close(world)
+    dist.destroy_process_group()
+
+
+def test_shared_host_buffer_world_size_2_gloo(tmp_path):
+    """The shared page-locked stem buffer of the multi-GPU host path (CUDA registration is left out on CPU)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'whole.pt')
+    port = 29500 + (os.getpid() + 17) % 1000
+    mp.spawn(_shared_host_worker, args=(2, port, out), nprocs=2, join=True)
+    assert torch.equal(torch.load(out)[0], torch.arange(1000, dtype=torch.float32))
+
+
 def test_shard_plan_tiles_the_track():
     from lib import distributed
     for T in (431, 1292, 10336, 20672, 82688, 103360):

@@ -81,6 +81,104 @@ def release(ctx):
     _calls.pop(ctx, None)
 
 
+class SharedHostBuffer(object):
+    """One page-locked host buffer shared by all ranks of the node: a POSIX shared-memory segment that every rank maps and
+    registers with CUDA (``cudaHostRegister``), so that the device-to-host copy of each rank's span lands in the SAME
+    buffer and the host-buffer form of the path (``separate_wave_host``) returns assembled stems on every rank - the host
+    counterpart of the peer-mapped stem buffers of the device-resident form.
+
+    Collective: build it with ``SharedHostBuffer.create`` on every rank.  ``create`` returns None on EVERY rank when any
+    rank fails a step (no /dev/shm, registration refused, ...); callers then fall back to per-rank pinned buffers."""
+
+    def __init__(self):
+        self.shm = None
+        self.tensor = None
+        self.registered = False
+        self.owner = False
+
+    @staticmethod
+    def _agree(ok, world, group):
+        import torch.distributed as dist
+        if world == 1:
+            return bool(ok)
+        on_gpu = dist.get_backend(group) == 'nccl'
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device='cuda' if on_gpu else 'cpu')
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        return bool(t.item())
+
+    @classmethod
+    def create(cls, shape, world, rank, group=None, register=None):
+        """float32 buffer of ``shape``; register=None registers with CUDA when a device is available."""
+        import numpy as np
+        from multiprocessing import shared_memory
+        self = cls()
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = max(4, 4 * n)
+        names = [None]
+        ok = True
+        try:
+            if rank == 0:
+                self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                self.owner = True
+                names[0] = self.shm.name
+        except Exception:
+            ok = False
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(names, src=0, group=group)
+        ok = ok and names[0] is not None
+        try:
+            if ok and rank != 0:
+                self.shm = shared_memory.SharedMemory(name=names[0])
+                try:   # the creator unlinks the segment; keep this process's resource tracker from doing it as well
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, 'shared_memory')
+                except Exception:
+                    pass
+            if ok:
+                arr = np.ndarray((n,), dtype=np.float32, buffer=self.shm.buf)
+                self.tensor = torch.from_numpy(arr).view(*[int(d) for d in shape])
+                if register is None:
+                    register = torch.cuda.is_available()
+                if register:
+                    rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+                    self.registered = int(rc) == 0
+                    ok = self.registered and self.tensor.is_pinned()
+        except Exception:
+            ok = False
+        if not cls._agree(ok, world, group):
+            self.close(world, group, collective=False)
+            return None
+        return self
+
+    def close(self, world=1, group=None, collective=True):
+        """Unregister and unmap; rank 0 removes the segment after every rank has let go of it."""
+        if self.registered:
+            try:
+                torch.cuda.synchronize()
+                torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            except Exception:
+                pass
+            self.registered = False
+        self.tensor = None
+        if collective and world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
+        if self.shm is not None:
+            if self.owner:
+                try:
+                    self.shm.unlink()
+                except Exception:
+                    pass
+            try:
+                self.shm.close()   # raises BufferError while a caller still holds a view; the mapping then goes with it
+            except Exception:
+                pass
+            self.shm = None
+
+
 class _RawCudaArray(object):
     """Zero-copy torch view of a raw device pointer (``torch.as_tensor`` reads __cuda_array_interface__)."""
 
