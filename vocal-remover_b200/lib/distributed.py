@@ -120,11 +120,26 @@ class SharedHostBuffer(object):
         ok = True
         try:
             if rank == 0:
+                # tmpfs pages are allocated on first touch and a full /dev/shm then raises SIGBUS: make sure the whole
+                # segment fits and reserve it up front (ENOSPC here instead of a bus error later)
+                st = os.statvfs('/dev/shm')
+                if st.f_bavail * st.f_frsize < nbytes + (64 << 20):
+                    raise OSError('not enough room in /dev/shm for %d bytes' % nbytes)
                 self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
                 self.owner = True
+                os.posix_fallocate(self.shm._fd, 0, nbytes)
                 names[0] = self.shm.name
         except Exception:
             ok = False
+            names[0] = None
+            if self.shm is not None:   # created but not reservable
+                try:
+                    self.shm.unlink()
+                    self.shm.close()
+                except Exception:
+                    pass
+                self.shm = None
+                self.owner = False
         if world > 1:
             import torch.distributed as dist
             dist.broadcast_object_list(names, src=0, group=group)
