@@ -286,3 +286,21 @@ def test_align_wave_head_and_tail_recovers_a_known_delay():
     assert np.abs(b2[:, mid] - 0.7 * a2[:, mid]).max() < 1e-6
     t, (s0, s1) = spec_utils._trim_silence(a)
     assert s0 <= 3000 and s0 >= 3000 - 2048 and s1 >= 3000 + sr * 5 and t.shape[1] == s1 - s0
+
+
+def test_async_writer_matches_sync_write_and_reports_failures(tmp_path):
+    from lib import audio_io
+    rng = np.random.default_rng(0)
+    a = (0.5 * rng.standard_normal((4410, 2))).astype(np.float32)
+    b = (0.5 * rng.standard_normal((4410, 2))).astype(np.float32)
+    audio_io.write(str(tmp_path / 'a_sync.wav'), a, 44100)
+    w = audio_io.AsyncWriter()
+    w.write(str(tmp_path / 'a.wav'), a, 44100)
+    w.write(str(tmp_path / 'b.wav'), b, 44100)
+    w.join()
+    assert (tmp_path / 'a.wav').read_bytes() == (tmp_path / 'a_sync.wav').read_bytes()
+    xb, sr = audio_io.load(str(tmp_path / 'b.wav'), sr=44100, mono=False, dtype=np.float32)
+    assert sr == 44100 and xb.shape == (2, 4410) and np.abs(xb - np.clip(b.T, -1, 1)).max() < 2.0 / 32768
+    w.write(str(tmp_path / 'no_such_dir' / 'c.wav'), a, 44100)
+    with pytest.raises(Exception):
+        w.join()

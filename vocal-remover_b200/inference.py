@@ -214,8 +214,10 @@ def main():
     print('stft of wave source, separation, inverse stft of instruments and vocals...', end=' ')
     wave_inst, wave_voc = sp.separate_wave(X, tta=args.tta)
     print('done')
-    audio_io.write('{}{}_Instruments.wav'.format(output_dir, basename), wave_inst.T, sr)
-    audio_io.write('{}{}_Vocals.wav'.format(output_dir, basename), wave_voc.T, sr)
+    writer = audio_io.AsyncWriter()   # the two stems are encoded and written concurrently
+    writer.write('{}{}_Instruments.wav'.format(output_dir, basename), wave_inst.T, sr)
+    writer.write('{}{}_Vocals.wav'.format(output_dir, basename), wave_voc.T, sr)
+    writer.join()
 
 
 if __name__ == '__main__':

@@ -118,8 +118,42 @@ def write(path, data, sr):
     if data.ndim == 1:
         data = data[:, None]
     pcm = np.clip(np.round(data * 32767.0), -32768, 32767).astype('<i2')
-    with _wave.open(path, 'wb') as f:
+    with open(path, 'wb') as fh, _wave.open(fh, 'wb') as f:   # a bad path fails in open(), before a Wave_write exists
         f.setnchannels(pcm.shape[1])
         f.setsampwidth(2)
         f.setframerate(sr)
         f.writeframes(pcm.tobytes())
+
+
+class AsyncWriter(object):
+    """Encode and write stems on worker threads while the caller carries on (the two ``sf.write`` calls of
+    inference.py:173,178 are independent of each other and of the next file's separation); ``join`` re-raises the first
+    failure.  The arrays are written as passed: do not modify them before ``join``."""
+
+    def __init__(self):
+        import threading
+        self._threading = threading
+        self._jobs = []
+
+    def write(self, path, data, sr):
+        box = {}
+
+        def run():
+            try:
+                write(path, data, sr)
+            except BaseException as exc:   # handed to join()
+                box['exc'] = exc
+
+        t = self._threading.Thread(target=run, name='vr-write')
+        t.start()
+        self._jobs.append((t, box))
+
+    def join(self):
+        jobs, self._jobs = self._jobs, []
+        first = None
+        for t, box in jobs:
+            t.join()
+            if first is None and 'exc' in box:
+                first = box['exc']
+        if first is not None:
+            raise first
