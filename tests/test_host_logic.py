@@ -304,3 +304,33 @@ def test_async_writer_matches_sync_write_and_reports_failures(tmp_path):
     w.write(str(tmp_path / 'no_such_dir' / 'c.wav'), a, 44100)
     with pytest.raises(Exception):
         w.join()
+
+
+def test_cache_or_load_layout_and_cache_hit(tmp_path, monkeypatch):
+    """spec_utils.cache_or_load (reference lib/spec_utils.py:122-154): cache directory / file layout, the (T, 2, bins)
+    on-disk transpose, and the second call served from the cache.  The GPU STFT is replaced by the CPU oracle here."""
+    from lib import audio_io, spec_utils
+    from oracle import stft_oracle
+    calls = []
+
+    def cpu_stft(wave, hop_length, n_fft):
+        calls.append(wave.shape)
+        return stft_oracle.wave_to_spectrogram(wave, hop_length, n_fft)
+
+    monkeypatch.setattr(spec_utils, 'wave_to_spectrogram', cpu_stft)
+    rng = np.random.default_rng(1)
+    sr = 8000
+    inst = (0.3 * np.sin(2 * np.pi * 440 * np.arange(2 * sr) / sr))[None, :].repeat(2, 0)
+    voc = 0.2 * rng.standard_normal((2, 2 * sr))
+    mix_dir, inst_dir = tmp_path / 'mixtures', tmp_path / 'instruments'
+    mix_dir.mkdir()
+    inst_dir.mkdir()
+    audio_io.write(str(mix_dir / 'song.wav'), (inst + voc).T, sr)
+    audio_io.write(str(inst_dir / 'song.wav'), inst.T, sr)
+    X, y, pm, pi = spec_utils.cache_or_load(str(mix_dir / 'song.wav'), str(inst_dir / 'song.wav'), sr, 128, 256)
+    assert pm == str(mix_dir / 'sr8000_hl128_nf256' / 'song.npy') and pi == str(inst_dir / 'sr8000_hl128_nf256' / 'song.npy')
+    assert X.shape == y.shape and X.shape[:2] == (2, 129) and X.dtype == np.complex64
+    assert np.load(pm).shape == (X.shape[2], 2, 129) and len(calls) == 2
+    X2, y2, _, _ = spec_utils.cache_or_load(str(mix_dir / 'song.wav'), str(inst_dir / 'song.wav'), sr, 128, 256)
+    assert len(calls) == 2                                # cache hit: no transform
+    assert np.array_equal(X2, X) and np.array_equal(y2, y)

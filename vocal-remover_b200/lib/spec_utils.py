@@ -171,3 +171,34 @@ def align_wave_head_and_tail(a, b, sr):
     else:
         a = a[:, :b.shape[1]]
     return a, b
+
+
+def cache_or_load(mix_path, inst_path, sr, hop_length, n_fft):
+    """lib/spec_utils.py:122-154: spectrograms of a (mixture, instruments) pair, cached next to the audio.
+
+    The cache layout is the reference's - ``<dir>/sr{sr}_hl{hop}_nf{n_fft}/<basename>.npy`` holding the spectrogram
+    transposed to (T, 2, bins) - so caches written by either implementation are interchangeable.  On a miss both files
+    are decoded (non-``sr`` input is converted on the GPU, lib/audio_io.py), aligned and transformed with the GPU STFT.
+    Returns (X, y, mix_cache_path, inst_cache_path) with X, y complex64 of shape (2, bins, T)."""
+    import os
+    from . import audio_io
+    cache_dir = 'sr{}_hl{}_nf{}'.format(sr, hop_length, n_fft)
+    paths = []
+    for src in (mix_path, inst_path):
+        d = os.path.join(os.path.dirname(src), cache_dir)
+        os.makedirs(d, exist_ok=True)
+        paths.append(os.path.join(d, os.path.splitext(os.path.basename(src))[0] + '.npy'))
+    mix_cache_path, inst_cache_path = paths
+    if os.path.exists(mix_cache_path) and os.path.exists(inst_cache_path):
+        X = np.load(mix_cache_path).transpose(1, 2, 0)
+        y = np.load(inst_cache_path).transpose(1, 2, 0)
+    else:
+        X, _ = audio_io.load(mix_path, sr=sr, mono=False, dtype=np.float32, device=_DEVICE_INDEX)
+        y, _ = audio_io.load(inst_path, sr=sr, mono=False, dtype=np.float32, device=_DEVICE_INDEX)
+        X, y = align_wave_head_and_tail(X, y, sr)
+        X = wave_to_spectrogram(X, hop_length, n_fft)
+        y = wave_to_spectrogram(y, hop_length, n_fft)
+        np.save(mix_cache_path, X.transpose(2, 0, 1))
+        np.save(inst_cache_path, y.transpose(2, 0, 1))
+    assert X.shape == y.shape
+    return X, y, mix_cache_path, inst_cache_path
