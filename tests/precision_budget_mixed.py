@@ -6,7 +6,7 @@ of bf16's 2^-9, so the fp8 rounding of the corrections weighs 8x less than in pr
 half product runs at the bf16 rate and the two kind::f8f6f4 products at twice that rate: 1 + 1/2 + 1/2 = 2 units of tensor
 time per product instead of 3, i.e. the roofline bound moves from 0.33 to 0.50, and an activation still costs 4 bytes
 (half hi + fp8 lo + fp8 copy of hi).  Measured, every layer at once (profiles/r02_precision_budget_mixed.txt):
-corrections in half 9.9e-6, in e4m3 2.7e-4 (gate 1e-3), in e5m2 5.5e-4.
+corrections in half 9.9e-6, in e4m3 2.7e-4 (gate 1e-3), in e5m2 5.5e-4, in block-scaled fp4 (a 1.5-unit scheme) 1.4e-3 - too coarse.
 Usage: python tests/precision_budget_mixed.py"""
 import os, sys, numpy as np, torch, torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -20,6 +20,23 @@ def q(x, dt, top):
     if m == 0.0: return x
     s = 2.0 ** np.floor(np.log2(top / m))
     return (x * s).to(dt).to(torch.float32) / s
+GRID4 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+
+
+def q4_blocks(x, dim=1, blk=32):
+    """block-scaled fp4 (e2m1 magnitudes, one power-of-two scale per 32 channels: mxfp4-like) along the reduction dim"""
+    x = x.movedim(dim, -1).contiguous()
+    shp = x.shape
+    c = shp[-1]
+    pad = (-c) % blk
+    xp = F.pad(x, (0, pad)).reshape(*shp[:-1], (c + pad) // blk, blk)
+    m = xp.abs().amax(dim=-1, keepdim=True).clamp(min=1e-30)
+    s = torch.exp2(torch.floor(torch.log2(6.0 / m)))
+    a = (xp * s).abs().clamp(max=6.0).contiguous()
+    y = torch.sign(xp) * GRID4[torch.bucketize(a, (GRID4[1:] + GRID4[:-1]) / 2)] / s
+    return y.reshape(*shp[:-1], c + pad)[..., :c].movedim(-1, dim)
+
+
 MODE = {'m': None}
 TOP = {'t': 256.0}
 def conv(sd, p, x, stride=1, pad=1, dil=1, act='relu'):
@@ -35,6 +52,8 @@ def conv(sd, p, x, stride=1, pad=1, dil=1, act='relu'):
         f = lambda t: q(t, torch.float8_e4m3fn, TOP['t'])
     elif md == 'e5m2':
         f = lambda t: q(t, torch.float8_e5m2, 16384.0)
+    elif md == 'mxfp4':
+        f = q4_blocks
     else:
         f = h16
     y = F.conv2d(xh, wh, None, **kw) + F.conv2d(f(xl), f(wh), None, **kw) + F.conv2d(f(xh), f(wl), None, **kw)
@@ -51,7 +70,7 @@ Xp = np.pad(X, ((0, 0), (0, 0), (pad_l, pad_r))); Xp /= np.abs(X).max()
 wins = [torch.from_numpy(np.abs(Xp[None, :, :, i * roi:i * roi + 256]).astype(np.float32)) for i in range(4)]
 refs = [net_oracle.forward(sd, w) for w in wins]
 net_oracle.conv_bn_act = conv
-for md in ('half', 'e4m3', 'e5m2'):
+for md in ('half', 'e4m3', 'e5m2', 'mxfp4'):
     MODE['m'] = md
     print('half hi*hi + corrections in %s\t%.3e' % (md, (net_oracle.forward(sd, wins[1]) - refs[1]).abs().max().item()), flush=True)
 # all four windows of the 10 s input, and per-tensor scales 8x / 64x smaller than the tightest one: a static, calibrated
